@@ -1,0 +1,186 @@
+/*
+ * include/pcnn.h -- C ABI of the B200-native LeNet/MNIST training engine (libpcnn.so).
+ *
+ * This is the drop-in boundary for the hot path of Tamerkobba/Parallel-CNN: the 18 layer functions of
+ * Sequential/layer.h and the driver entry points of Sequential/Main.cpp.  The reference has no FFI layer
+ * (its boundary is `#include "layer.h"`), so include/layer.h in this repo re-declares the reference's own
+ * class and functions and forwards each of them to the entry points below; INTEGRATION.md shows the binding.
+ * Every entry point cites the reference interface it replaces as  [ref: <file>:<lines>]  relative to
+ * /root/reference/.
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints.  No torch / C++ types.  All functions return 0 on success or a negative
+ *     pcnn_status; pcnn_last_error_string() describes the most recent failure on the calling thread.
+ *   - "dev" pointers are CUDA device pointers on the context's device; "host" pointers are ordinary memory.
+ *   - every call enqueues on the context's stream; only *_sync / *_d2h / get_* / *_host calls block.
+ *   - one context per GPU, not thread-safe per context (the reference is single-threaded global state).
+ *   - there is NO CPU fallback: on a machine without a usable sm_100 GPU pcnn_create fails with
+ *     PCNN_ERR_NOGPU and nothing else computes.
+ *
+ * Packed parameter vector (PCNN_NPARAM = 2,343 floats), also the layout of the packed gradient:
+ *     [0,150) c1.weight[6][5][5] | [150,156) c1.bias | [156,172) s1.weight[1][4][4] | [172] s1.bias |
+ *     [173,2333) f.weight[10][6][6][6] | [2333,2343) f.bias             [ref: Sequential/Main.cpp:17-20]
+ * The packed gradient holds what the reference multiplies by dt (the NEGATIVE gradient, layer.h:93): d_weight
+ * for the weight blocks and the raw bias accumulators (sum d_preact) for the bias blocks; the /576 and /216
+ * of layer.h:412 and layer.h:316 are applied by the update.  Element PCNN_NPARAM of the device-side vector
+ * carries the sum of per-sample error norms (Main.cpp:168-169).
+ */
+#ifndef PCNN_H_
+#define PCNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCNN_NPARAM 2343
+#define PCNN_OFF_C1W 0
+#define PCNN_OFF_C1B 150
+#define PCNN_OFF_S1W 156
+#define PCNN_OFF_S1B 172
+#define PCNN_OFF_FW 173
+#define PCNN_OFF_FB 2333
+#define PCNN_IMG 784   /* 28 x 28 */
+#define PCNN_C1 3456   /* 6 x 24 x 24 */
+#define PCNN_S1 216    /* 6 x 6 x 6 */
+#define PCNN_F 10
+
+typedef enum {
+    PCNN_OK = 0,
+    PCNN_ERR_ARG = -1,    /* null pointer, negative size, bad enum */
+    PCNN_ERR_CUDA = -2,   /* a CUDA runtime call or kernel failed */
+    PCNN_ERR_NCCL = -3,   /* NCCL missing or a collective failed */
+    PCNN_ERR_STATE = -4,  /* call not valid in the current state (no dataset bound, comm not initialised...) */
+    PCNN_ERR_IO = -5,     /* file problems other than the mnist_load codes */
+    PCNN_ERR_NOGPU = -6   /* no CUDA device / not compute capability 10.x */
+} pcnn_status;
+
+typedef enum { PCNN_U8 = 0, PCNN_F32 = 1 } pcnn_pixel_type;   /* IDX bytes, or the reference's float[28][28] */
+typedef enum { PCNN_TRAIN_SET = 0, PCNN_TEST_SET = 1 } pcnn_split;
+
+typedef struct pcnn_ctx pcnn_ctx;
+
+/* ------------------------------------------------------------------ library / context */
+int pcnn_version(void);
+const char *pcnn_last_error_string(void);
+/* device < 0: current device.  stream: a cudaStream_t to enqueue on (e.g. the caller's torch stream) or NULL
+ * for a private non-blocking stream. */
+int pcnn_create(pcnn_ctx **out, int device, void *stream);
+int pcnn_destroy(pcnn_ctx *ctx);
+int pcnn_sync(pcnn_ctx *ctx);
+int pcnn_device_info(pcnn_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes);
+
+/* ------------------------------------------------------------------ device buffers owned by `Layer`
+ * [ref: Sequential/layer.h:39-79  Layer::Layer / ~Layer / setOutput / clear / bp_clear] */
+int pcnn_malloc(pcnn_ctx *ctx, void **dev, size_t bytes);             /* zero-initialised, like new float[n]() */
+int pcnn_free(pcnn_ctx *ctx, void *dev);
+int pcnn_memset0(pcnn_ctx *ctx, void *dev, size_t bytes);            /* Layer::clear, Layer::bp_clear */
+int pcnn_h2d(pcnn_ctx *ctx, void *dev, const void *host, size_t bytes);   /* Layer::setOutput (blocking) */
+int pcnn_d2h(pcnn_ctx *ctx, void *host, const void *dev, size_t bytes);   /* host reads of l_f.output etc. */
+int pcnn_d2d(pcnn_ctx *ctx, void *dst, const void *src, size_t bytes);
+
+/* ------------------------------------------------------------------ parameters
+ * pcnn_init_params_reference replays the constructor draws of the three static Layer objects: glibc rand()
+ * with the default seed, per neuron bias then weights, c1 -> s1 -> f  [ref: layer.h:48-54, Main.cpp:17-20].
+ * It is a host-side utility (private re-implementation of the glibc TYPE_3 generator; global rand() state
+ * is not touched) and needs no GPU. */
+int pcnn_init_params_reference(float *host_params);
+int pcnn_set_params(pcnn_ctx *ctx, const float *host_params);
+int pcnn_get_params(pcnn_ctx *ctx, float *host_params);
+int pcnn_get_grads(pcnn_ctx *ctx, float *host_grads);                /* packed gradient of the last step */
+int pcnn_params_dev(pcnn_ctx *ctx, float **dev_params);              /* the context's own packed vector */
+int pcnn_set_learning_rate(pcnn_ctx *ctx, float dt);                 /* default 0.1f  [ref: layer.h:12] */
+/* 9,372-byte packed checkpoint with a 16-byte header (the reference has none) */
+int pcnn_save_params(pcnn_ctx *ctx, const char *path);
+int pcnn_load_params(pcnn_ctx *ctx, const char *path);
+
+/* ------------------------------------------------------------------ per-operator API (drop-in for layer.h)
+ * Device pointers; row-major arrays shaped as in the reference with a leading batch dimension B (B = 1 is the
+ * reference call).  Arithmetic follows the reference's evaluation order in fp32 without FMA contraction and
+ * evaluates the sigmoid in double, so B = 1 results are bit-identical to Sequential/layer.h up to the last-ulp
+ * difference between CUDA's and glibc's double exp().  For B > 1 the weight-gradient ops sum over the batch
+ * and the in-place bias updates use dt / B (DESIGN.md "mini-batch semantics"). */
+int pcnn_apply_step_function(pcnn_ctx *ctx, const float *in, float *out, long n);        /* [ref: layer.h:85-89] */
+int pcnn_make_error(pcnn_ctx *ctx, float *err, const float *out, unsigned Y, int n);     /* [ref: layer.h:91-95] */
+int pcnn_make_error_batch(pcnn_ctx *ctx, float *err, const float *out, const uint8_t *labels, int B);
+int pcnn_apply_grad(pcnn_ctx *ctx, float *w, const float *g, long n);                    /* [ref: layer.h:97-101] */
+int pcnn_apply_grad_scaled(pcnn_ctx *ctx, float *w, const float *g, long n, float step);
+int pcnn_vector_norm(pcnn_ctx *ctx, const float *v, int n, int B, float *norms_dev);     /* [ref: Main.cpp:28-34] */
+int pcnn_fp_c1(pcnn_ctx *ctx, const float *in, float *pre, const float *w, const float *b, int B);   /* [ref: layer.h:105-140] */
+int pcnn_fp_s1(pcnn_ctx *ctx, const float *in, float *pre, const float *w, const float *b, int B);   /* [ref: layer.h:143-181] */
+int pcnn_fp_preact_f(pcnn_ctx *ctx, const float *in, float *pre, const float *w, int B);             /* [ref: layer.h:184-203] */
+int pcnn_fp_bias_f(pcnn_ctx *ctx, float *pre, const float *b, int B);                                /* [ref: layer.h:206-211] */
+int pcnn_bp_weight_f(pcnn_ctx *ctx, float *dw, const float *dpre, const float *pout, int B);         /* [ref: layer.h:214-227] */
+int pcnn_bp_bias_f(pcnn_ctx *ctx, float *bias, const float *dpre, int B);                            /* [ref: layer.h:229-234] */
+int pcnn_bp_output_s1(pcnn_ctx *ctx, float *dout, const float *nw, const float *ndpre, int B);       /* [ref: layer.h:237-257] */
+int pcnn_bp_preact_s1(pcnn_ctx *ctx, float *dpre, const float *dout, const float *pre, int B);       /* [ref: layer.h:260-270] */
+int pcnn_bp_weight_s1(pcnn_ctx *ctx, float *dw, const float *dpre, const float *pout, int B);        /* [ref: layer.h:272-300] */
+int pcnn_bp_bias_s1(pcnn_ctx *ctx, float *bias, const float *dpre, int B);                           /* [ref: layer.h:302-317] */
+int pcnn_bp_output_c1(pcnn_ctx *ctx, float *dout, const float *nw, const float *ndpre, int B);       /* [ref: layer.h:319-346] */
+int pcnn_bp_preact_c1(pcnn_ctx *ctx, float *dpre, const float *dout, const float *pre, int B);       /* [ref: layer.h:348-369] */
+int pcnn_bp_weight_c1(pcnn_ctx *ctx, float *dw, const float *dpre, const float *pout, int B);        /* [ref: layer.h:371-395] */
+int pcnn_bp_bias_c1(pcnn_ctx *ctx, float *bias, const float *dpre, int B);                           /* [ref: layer.h:398-414] */
+
+/* ------------------------------------------------------------------ data  [ref: Sequential/mnist.h:79-160, Main.cpp:36-42]
+ * pcnn_mnist_load_u8 keeps mnist_load's return codes (0 ok, -1 no such files, -2 bad image file, -3 bad label
+ * file, -4 count mismatch) but returns the raw u8 pixels instead of the double[28][28] staging. */
+int pcnn_mnist_load_u8(const char *image_file, const char *label_file, uint8_t **images, uint8_t **labels,
+                       unsigned *count);
+void pcnn_mnist_free(void *p);
+/* copy a host dataset to the device and bind it as the train / test split (u8 IDX payload or float[784]) */
+int pcnn_dataset_upload(pcnn_ctx *ctx, int split, const void *host_images, int pixel_type,
+                        const uint8_t *host_labels, long n);
+/* bind caller-owned device buffers instead (no copy; caller keeps them alive) */
+int pcnn_dataset_bind(pcnn_ctx *ctx, int split, const void *dev_images, int pixel_type,
+                      const uint8_t *dev_labels, long n);
+
+/* ------------------------------------------------------------------ fused training / evaluation path
+ * One step = forward_pass + makeError + vectorNorm + back_pass for every sample of the batch with frozen
+ * parameters, batch-sum of the packed gradient, (optional all-reduce), update  w += (dt / B_global) * g.
+ * At B = 1 this is the body of learn()'s loop  [ref: Main.cpp:157-171, 59-144]. */
+int pcnn_train_step(pcnn_ctx *ctx, long first, int B);                 /* samples [first, first+B) of the bound train split */
+int pcnn_train_steps(pcnn_ctx *ctx, long first, int B, int nsteps);    /* consecutive batches, wrapping at the end of the split */
+int pcnn_train_step_dev(pcnn_ctx *ctx, const void *dev_images, int pixel_type, const uint8_t *dev_labels, int B);
+/* host buffers in, H2D inside the call, error-norm sum of the step back out (blocking) */
+int pcnn_train_step_host(pcnn_ctx *ctx, const void *host_images, int pixel_type, const uint8_t *host_labels,
+                         int B, float *err_sum_out);
+/* frozen-parameter gradient only (no update): fills the packed gradient (+ error sum); used by parity tests */
+int pcnn_compute_grads(pcnn_ctx *ctx, const void *dev_images, int pixel_type, const uint8_t *dev_labels, int B);
+/* learn(): `epochs` passes over the bound train split in dataset order with batch B (tail batch kept);
+ * mean_err_out = sum of error norms / n of the LAST epoch, as learn() prints  [ref: Main.cpp:146-184] */
+int pcnn_learn(pcnn_ctx *ctx, int B, int epochs, float *mean_err_out);
+/* same, streaming the dataset from host memory through a double-buffered H2D pipeline */
+int pcnn_learn_host(pcnn_ctx *ctx, const void *host_images, int pixel_type, const uint8_t *host_labels,
+                    long n, int B, int epochs, float *mean_err_out);
+int pcnn_err_sum(pcnn_ctx *ctx, double *sum_out, int reset);           /* running sum of per-sample error norms */
+/* forward_pass for B samples; f_out_dev [B][10] may be NULL, pred_dev [B] (first-max argmax) may be NULL
+ * [ref: Main.cpp:59-105, 186-200] */
+int pcnn_forward_batch(pcnn_ctx *ctx, const void *dev_images, int pixel_type, int B, float *f_out_dev,
+                       uint8_t *pred_dev);
+/* test(): misclassification count over the bound test split  [ref: Main.cpp:202-214] */
+int pcnn_test(pcnn_ctx *ctx, long *wrong_out);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int pcnn_launch_count(pcnn_ctx *ctx, long *count_out);
+
+/* ------------------------------------------------------------------ data parallelism (not in the reference)
+ * Sample-sharded replicas, one process per GPU.  After pcnn_comm_init_rank every train step all-reduces the
+ * packed gradient (2,344 floats) once and divides the step by B * world. */
+int pcnn_comm_unique_id(void *id_out, size_t *id_bytes);               /* rank 0; 128 bytes */
+int pcnn_comm_init_rank(pcnn_ctx *ctx, const void *id, int rank, int world);
+int pcnn_comm_destroy(pcnn_ctx *ctx);
+int pcnn_allreduce_grads(pcnn_ctx *ctx);
+
+/* ------------------------------------------------------------------ north_star extension ops (parity unpinned by the reference)
+ * max-pool k x k stride k over [C][H][W] planes with argmax cache (flat index i*k+j, first maximum wins) */
+int pcnn_maxpool_fwd(pcnn_ctx *ctx, const float *in, float *out, int32_t *argmax, int planes, int H, int W, int k);
+int pcnn_maxpool_bwd(pcnn_ctx *ctx, const float *dout, const int32_t *argmax, float *din, int planes, int H, int W, int k);
+/* softmax cross-entropy over n logits per row; d = onehot - p (the reference's sign convention for d_preact) */
+int pcnn_softmax_ce(pcnn_ctx *ctx, const float *logits, const uint8_t *labels, int B, int n, float *prob,
+                    float *d, float *loss);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCNN_H_ */

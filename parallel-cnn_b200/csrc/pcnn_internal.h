@@ -1,0 +1,119 @@
+// parallel-cnn_b200/csrc/pcnn_internal.h -- shared declarations of the libpcnn.so translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <map>
+#include <tuple>
+
+#include "../../include/pcnn.h"
+
+#define PCNN_VERSION_NUMBER 100   /* 0.1.0 */
+
+// Packed vectors on the device carry one extra float: the batch sum of per-sample error norms.
+constexpr int NPARAM = PCNN_NPARAM;
+constexpr int NPACK = NPARAM + 1;           // 2344 floats = 9376 B, a multiple of 16 B (bulk-copy granule)
+constexpr int OFF_C1W = PCNN_OFF_C1W, OFF_C1B = PCNN_OFF_C1B, OFF_S1W = PCNN_OFF_S1W, OFF_S1B = PCNN_OFF_S1B,
+              OFF_FW = PCNN_OFF_FW, OFF_FB = PCNN_OFF_FB, OFF_ERR = PCNN_NPARAM;
+
+// Fused-step launch geometry (see fused_kernels.cu)
+constexpr int FUSED_THREADS = 224;          // 216 workers (one per (map, 4x4 window)) + 8 helpers
+constexpr int FUSED_WORKERS = 216;
+constexpr int FUSED_CTAS_PER_SM = 2;
+constexpr int MAX_SLOTS = 148 * 4;          // upper bound on the fused grid (per-CTA partial-gradient slots)
+
+struct pcnn_split_binding {
+    const void *images = nullptr;           // device
+    const uint8_t *labels = nullptr;        // device
+    int pixel_type = PCNN_U8;
+    long n = 0;
+    void *owned_images = nullptr;           // non-null when uploaded through pcnn_dataset_upload
+    void *owned_labels = nullptr;
+};
+
+struct pcnn_graph_key {
+    int B, nsteps, world, pixel_type;
+    const void *images;
+    long n;
+    bool operator<(const pcnn_graph_key &o) const {
+        return std::tie(B, nsteps, world, pixel_type, images, n) <
+               std::tie(o.B, o.nsteps, o.world, o.pixel_type, o.images, o.n);
+    }
+};
+
+struct pcnn_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t hbm_bytes = 0;
+    float lr = 1.0E-01f;                    // dt, layer.h:12
+
+    float *d_params = nullptr;              // [NPACK]
+    float *d_grads = nullptr;               // [NPACK] packed gradient (+ error sum) of the last step
+    float *d_slots = nullptr;               // [MAX_SLOTS][NPACK] per-CTA partial gradients
+    double *d_err_total = nullptr;          // running sum of error norms (double)
+    long long *d_cursor = nullptr;          // next global sample index for cursor-driven steps
+    int *d_wrong = nullptr;                 // misclassification counter of pcnn_test
+    float *d_step_err = nullptr;            // [step_err_cap] per-step error sums for pcnn_learn_host
+    long step_err_cap = 0;
+
+    pcnn_split_binding split[2];
+
+    // host staging for the *_host entry points (pinned)
+    void *h_stage[2] = {nullptr, nullptr};
+    void *d_stage[2] = {nullptr, nullptr};
+    uint8_t *h_stage_lab[2] = {nullptr, nullptr};
+    uint8_t *d_stage_lab[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    long stage_cap_samples = 0;
+    float *h_scalar = nullptr;              // pinned scratch for blocking scalar read-backs
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+
+    std::map<pcnn_graph_key, cudaGraphExec_t> graphs;
+
+    // data parallel state
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+
+    long launches = 0;
+};
+
+// ---- error plumbing ------------------------------------------------------------------------------------
+void pcnn_set_error(const char *fmt, ...);
+int pcnn_fail_cuda(cudaError_t e, const char *what, const char *file, int line);
+
+#define PCNN_CUDA(expr)                                                          \
+    do {                                                                         \
+        cudaError_t e__ = (expr);                                                \
+        if (e__ != cudaSuccess) return pcnn_fail_cuda(e__, #expr, __FILE__, __LINE__); \
+    } while (0)
+#define PCNN_REQUIRE(cond, code, ...)                                            \
+    do {                                                                         \
+        if (!(cond)) { pcnn_set_error(__VA_ARGS__); return (code); }             \
+    } while (0)
+#define PCNN_CHECK_LAUNCH(ctx)                                                   \
+    do {                                                                         \
+        (ctx)->launches++;                                                       \
+        cudaError_t e__ = cudaGetLastError();                                    \
+        if (e__ != cudaSuccess) return pcnn_fail_cuda(e__, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+struct pcnn_device_guard {
+    int prev = -1;
+    explicit pcnn_device_guard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~pcnn_device_guard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---- internal launchers shared between translation units -------------------------------------------------
+// fused_kernels.cu
+int pcnn_fused_configure();
+int pcnn_launch_fused_grad(pcnn_ctx *ctx, const void *images, int pixel_type, const uint8_t *labels,
+                           long n_total, long first, int B, bool use_cursor, int *grid_out);
+int pcnn_launch_reduce(pcnn_ctx *ctx, int grid_slots, int B, bool use_cursor, long n_total, bool update,
+                       float *step_err_out);
+int pcnn_launch_update(pcnn_ctx *ctx, int B, bool use_cursor, long n_total);
+// comm.cu
+int pcnn_comm_allreduce_packed(pcnn_ctx *ctx);

@@ -1,0 +1,294 @@
+"""Engine: a thin object wrapper over one pcnn_ctx.  Method names follow include/pcnn.h minus the pcnn_ prefix, which
+in turn follow /root/reference/Sequential/layer.h and Main.cpp (fp_c1, bp_weight_c1, learn, test ...)."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import F32, NPARAM, TEST_SET, TRAIN_SET, U8, PcnnError, check, lib
+
+
+def _pixel_type(arr_or_dtype):
+    dt = np.dtype(getattr(arr_or_dtype, "dtype", arr_or_dtype))
+    if dt == np.uint8:
+        return U8
+    if dt == np.float32:
+        return F32
+    raise PcnnError("pixel_type", -1, f"images must be uint8 or float32, got {dt}")
+
+
+class DeviceArray:
+    """A device buffer obtained from pcnn_malloc (zero-initialised like the reference's `new float[n]()`)."""
+
+    def __init__(self, engine, shape, dtype=np.float32):
+        self.engine = engine
+        self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check("pcnn_malloc", lib().pcnn_malloc(engine.ctx, C.byref(p), self.nbytes))
+        self.ptr = p.value
+
+    @classmethod
+    def from_host(cls, engine, host):
+        host = np.ascontiguousarray(host)
+        d = cls(engine, host.shape, host.dtype)
+        d.copy_from(host)
+        return d
+
+    def copy_from(self, host):
+        host = np.ascontiguousarray(host, self.dtype)
+        assert host.nbytes == self.nbytes, (host.shape, self.shape)
+        check("pcnn_h2d", lib().pcnn_h2d(self.engine.ctx, self.ptr, host.ctypes.data, self.nbytes))
+        return self
+
+    def to_host(self):
+        out = np.empty(self.shape, self.dtype)
+        check("pcnn_d2h", lib().pcnn_d2h(self.engine.ctx, out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+    def zero(self):
+        check("pcnn_memset0", lib().pcnn_memset0(self.engine.ctx, self.ptr, self.nbytes))
+
+    def free(self):
+        if self.ptr and self.engine.ctx:
+            lib().pcnn_free(self.engine.ctx, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _p(x):
+    """device pointer of a DeviceArray / raw int / torch tensor (data_ptr) / None"""
+    if x is None:
+        return None
+    if isinstance(x, DeviceArray):
+        return x.ptr
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return int(x)
+
+
+class Engine:
+    def __init__(self, device=-1, stream=None):
+        self.ctx = None
+        ctx = C.c_void_p()
+        check("pcnn_create", lib().pcnn_create(C.byref(ctx), int(device), stream))
+        self.ctx = ctx
+
+    def close(self):
+        if self.ctx:
+            lib().pcnn_destroy(self.ctx)
+            self.ctx = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _call(self, name, *args):
+        check(name, getattr(lib(), name)(self.ctx, *args))
+
+    # ------------------------------------------------------------------ context / parameters
+    def sync(self):
+        self._call("pcnn_sync")
+
+    def device_info(self):
+        sm, ma, mi, hb = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        self._call("pcnn_device_info", C.byref(sm), C.byref(ma), C.byref(mi), C.byref(hb))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value), hbm_bytes=hb.value)
+
+    def array(self, shape, dtype=np.float32):
+        return DeviceArray(self, shape, dtype)
+
+    def to_device(self, host):
+        return DeviceArray.from_host(self, host)
+
+    def set_params(self, p):
+        p = np.ascontiguousarray(p, np.float32)
+        assert p.size == NPARAM
+        self._call("pcnn_set_params", p.ctypes.data)
+
+    def get_params(self):
+        p = np.empty(NPARAM, np.float32)
+        self._call("pcnn_get_params", p.ctypes.data)
+        return p
+
+    def get_grads(self):
+        g = np.empty(NPARAM, np.float32)
+        self._call("pcnn_get_grads", g.ctypes.data)
+        return g
+
+    def params_dev(self):
+        p = C.c_void_p()
+        self._call("pcnn_params_dev", C.byref(p))
+        return p.value
+
+    def set_learning_rate(self, dt):
+        self._call("pcnn_set_learning_rate", float(dt))
+
+    def save_params(self, path):
+        self._call("pcnn_save_params", str(path).encode())
+
+    def load_params(self, path):
+        self._call("pcnn_load_params", str(path).encode())
+
+    def err_sum(self, reset=False):
+        s = C.c_double()
+        self._call("pcnn_err_sum", C.byref(s), 1 if reset else 0)
+        return s.value
+
+    def launch_count(self):
+        n = C.c_long()
+        self._call("pcnn_launch_count", C.byref(n))
+        return n.value
+
+    # ------------------------------------------------------------------ per-operator API (layer.h names)
+    def apply_step_function(self, inp, out, n):
+        self._call("pcnn_apply_step_function", _p(inp), _p(out), int(n))
+
+    def makeError(self, err, out, Y, n=10):
+        self._call("pcnn_make_error", _p(err), _p(out), int(Y), int(n))
+
+    def makeError_batch(self, err, out, labels, B):
+        self._call("pcnn_make_error_batch", _p(err), _p(out), _p(labels), int(B))
+
+    def apply_grad(self, w, g, n):
+        self._call("pcnn_apply_grad", _p(w), _p(g), int(n))
+
+    def vectorNorm(self, v, n, B, norms):
+        self._call("pcnn_vector_norm", _p(v), int(n), int(B), _p(norms))
+
+    def fp_c1(self, inp, pre, w, b, B=1):
+        self._call("pcnn_fp_c1", _p(inp), _p(pre), _p(w), _p(b), int(B))
+
+    def fp_s1(self, inp, pre, w, b, B=1):
+        self._call("pcnn_fp_s1", _p(inp), _p(pre), _p(w), _p(b), int(B))
+
+    def fp_preact_f(self, inp, pre, w, B=1):
+        self._call("pcnn_fp_preact_f", _p(inp), _p(pre), _p(w), int(B))
+
+    def fp_bias_f(self, pre, b, B=1):
+        self._call("pcnn_fp_bias_f", _p(pre), _p(b), int(B))
+
+    def bp_weight_f(self, dw, dpre, pout, B=1):
+        self._call("pcnn_bp_weight_f", _p(dw), _p(dpre), _p(pout), int(B))
+
+    def bp_bias_f(self, bias, dpre, B=1):
+        self._call("pcnn_bp_bias_f", _p(bias), _p(dpre), int(B))
+
+    def bp_output_s1(self, dout, nw, ndpre, B=1):
+        self._call("pcnn_bp_output_s1", _p(dout), _p(nw), _p(ndpre), int(B))
+
+    def bp_preact_s1(self, dpre, dout, pre, B=1):
+        self._call("pcnn_bp_preact_s1", _p(dpre), _p(dout), _p(pre), int(B))
+
+    def bp_weight_s1(self, dw, dpre, pout, B=1):
+        self._call("pcnn_bp_weight_s1", _p(dw), _p(dpre), _p(pout), int(B))
+
+    def bp_bias_s1(self, bias, dpre, B=1):
+        self._call("pcnn_bp_bias_s1", _p(bias), _p(dpre), int(B))
+
+    def bp_output_c1(self, dout, nw, ndpre, B=1):
+        self._call("pcnn_bp_output_c1", _p(dout), _p(nw), _p(ndpre), int(B))
+
+    def bp_preact_c1(self, dpre, dout, pre, B=1):
+        self._call("pcnn_bp_preact_c1", _p(dpre), _p(dout), _p(pre), int(B))
+
+    def bp_weight_c1(self, dw, dpre, pout, B=1):
+        self._call("pcnn_bp_weight_c1", _p(dw), _p(dpre), _p(pout), int(B))
+
+    def bp_bias_c1(self, bias, dpre, B=1):
+        self._call("pcnn_bp_bias_c1", _p(bias), _p(dpre), int(B))
+
+    # ------------------------------------------------------------------ data + fused path (Main.cpp names)
+    def dataset_upload(self, split, images, labels):
+        images = np.ascontiguousarray(images)
+        labels = np.ascontiguousarray(labels, np.uint8)
+        n = labels.shape[0]
+        assert images.size == n * 784
+        self._call("pcnn_dataset_upload", int(split), images.ctypes.data, _pixel_type(images), labels.ctypes.data, n)
+
+    def dataset_bind(self, split, images_dev, pixel_type, labels_dev, n):
+        self._call("pcnn_dataset_bind", int(split), _p(images_dev), int(pixel_type), _p(labels_dev), int(n))
+
+    def train_step(self, first, B):
+        self._call("pcnn_train_step", int(first), int(B))
+
+    def train_steps(self, first, B, nsteps):
+        self._call("pcnn_train_steps", int(first), int(B), int(nsteps))
+
+    def train_step_dev(self, images_dev, pixel_type, labels_dev, B):
+        self._call("pcnn_train_step_dev", _p(images_dev), int(pixel_type), _p(labels_dev), int(B))
+
+    def train_step_host(self, images, labels):
+        images = np.ascontiguousarray(images)
+        labels = np.ascontiguousarray(labels, np.uint8)
+        e = C.c_float()
+        self._call("pcnn_train_step_host", images.ctypes.data, _pixel_type(images), labels.ctypes.data,
+                   labels.shape[0], C.byref(e))
+        return e.value
+
+    def compute_grads(self, images_dev, pixel_type, labels_dev, B):
+        self._call("pcnn_compute_grads", _p(images_dev), int(pixel_type), _p(labels_dev), int(B))
+
+    def learn(self, B=1, epochs=1):
+        e = C.c_float()
+        self._call("pcnn_learn", int(B), int(epochs), C.byref(e))
+        return e.value
+
+    def learn_host(self, images, labels, B=1, epochs=1):
+        images = np.ascontiguousarray(images)
+        labels = np.ascontiguousarray(labels, np.uint8)
+        e = C.c_float()
+        self._call("pcnn_learn_host", images.ctypes.data, _pixel_type(images), labels.ctypes.data, labels.shape[0],
+                   int(B), int(epochs), C.byref(e))
+        return e.value
+
+    def forward_batch(self, images_dev, pixel_type, B, f_out_dev=None, pred_dev=None):
+        self._call("pcnn_forward_batch", _p(images_dev), int(pixel_type), int(B), _p(f_out_dev), _p(pred_dev))
+
+    def test(self):
+        w = C.c_long()
+        self._call("pcnn_test", C.byref(w))
+        return w.value
+
+    # ------------------------------------------------------------------ data parallel
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 256)()
+        n = C.c_size_t()
+        check("pcnn_comm_unique_id", lib().pcnn_comm_unique_id(buf, C.byref(n)))
+        return bytes(buf[: n.value])
+
+    def comm_init_rank(self, uid, rank, world):
+        self._call("pcnn_comm_init_rank", C.c_char_p(uid), int(rank), int(world))
+
+    def comm_destroy(self):
+        self._call("pcnn_comm_destroy")
+
+    def allreduce_grads(self):
+        self._call("pcnn_allreduce_grads")
+
+    # ------------------------------------------------------------------ extension ops
+    def maxpool_fwd(self, inp, out, argmax, planes, H, W, k):
+        self._call("pcnn_maxpool_fwd", _p(inp), _p(out), _p(argmax), int(planes), int(H), int(W), int(k))
+
+    def maxpool_bwd(self, dout, argmax, din, planes, H, W, k):
+        self._call("pcnn_maxpool_bwd", _p(dout), _p(argmax), _p(din), int(planes), int(H), int(W), int(k))
+
+    def softmax_ce(self, logits, labels, B, n, prob=None, d=None, loss=None):
+        self._call("pcnn_softmax_ce", _p(logits), _p(labels), int(B), int(n), _p(prob), _p(d), _p(loss))
+
+
+__all__ = ["Engine", "DeviceArray", "TRAIN_SET", "TEST_SET", "U8", "F32"]
