@@ -141,7 +141,10 @@ int pcnn_dataset_bind(pcnn_ctx *ctx, int split, const void *dev_images, int pixe
  * parameters, batch-sum of the packed gradient, (optional all-reduce), update  w += (dt / B_global) * g.
  * At B = 1 this is the body of learn()'s loop  [ref: Main.cpp:157-171, 59-144]. */
 int pcnn_train_step(pcnn_ctx *ctx, long first, int B);                 /* samples [first, first+B) of the bound train split */
-int pcnn_train_steps(pcnn_ctx *ctx, long first, int B, int nsteps);    /* consecutive batches, wrapping at the end of the split */
+/* consecutive batches starting at `first` (or continuing at the device-side cursor when first == -1), wrapping at the
+ * end of the split; replayed from cached CUDA graphs.  _prepare instantiates the graphs such a call needs (untimed). */
+int pcnn_train_steps(pcnn_ctx *ctx, long first, int B, int nsteps);
+int pcnn_train_steps_prepare(pcnn_ctx *ctx, int B, int nsteps);
 int pcnn_train_step_dev(pcnn_ctx *ctx, const void *dev_images, int pixel_type, const uint8_t *dev_labels, int B);
 /* host buffers in, H2D inside the call, error-norm sum of the step back out (blocking) */
 int pcnn_train_step_host(pcnn_ctx *ctx, const void *host_images, int pixel_type, const uint8_t *host_labels,
@@ -163,6 +166,13 @@ int pcnn_forward_batch(pcnn_ctx *ctx, const void *dev_images, int pixel_type, in
 int pcnn_test(pcnn_ctx *ctx, long *wrong_out);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int pcnn_launch_count(pcnn_ctx *ctx, long *count_out);
+/* per-step error sums recorded by the most recent pcnn_learn_host epoch (device -> pinned host, one float per step) */
+int pcnn_step_errs(pcnn_ctx *ctx, float *host_out, long cap, long *count_out);
+/* measurement helpers for bench.py (CUDA events on the context's stream, after `iters / 10 + 3` warm-up launches):
+ * average duration of the fused gradient kernel alone over `iters` launches walking the bound train split, and the
+ * sustained fp32 FMA rate of this GPU under its current clocks (dependent-chain-free FFMA micro-benchmark). */
+int pcnn_time_fused_kernel(pcnn_ctx *ctx, int B, int iters, float *avg_ms_out);
+int pcnn_measure_fp32_peak(pcnn_ctx *ctx, float *tflops_out);
 
 /* ------------------------------------------------------------------ data parallelism (not in the reference)
  * Sample-sharded replicas, one process per GPU.  After pcnn_comm_init_rank every train step all-reduces the

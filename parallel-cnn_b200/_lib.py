@@ -75,6 +75,7 @@ _SIG = {
     "pcnn_dataset_bind": [_vp, _i, _vp, _i, _vp, _l],
     "pcnn_train_step": [_vp, _l, _i],
     "pcnn_train_steps": [_vp, _l, _i, _i],
+    "pcnn_train_steps_prepare": [_vp, _i, _i],
     "pcnn_train_step_dev": [_vp, _vp, _i, _vp, _i],
     "pcnn_train_step_host": [_vp, _vp, _i, _vp, _i, C.POINTER(_f)],
     "pcnn_compute_grads": [_vp, _vp, _i, _vp, _i],
@@ -84,6 +85,9 @@ _SIG = {
     "pcnn_forward_batch": [_vp, _vp, _i, _i, _vp, _vp],
     "pcnn_test": [_vp, C.POINTER(_l)],
     "pcnn_launch_count": [_vp, C.POINTER(_l)],
+    "pcnn_step_errs": [_vp, _vp, _l, C.POINTER(_l)],
+    "pcnn_time_fused_kernel": [_vp, _i, _i, C.POINTER(_f)],
+    "pcnn_measure_fp32_peak": [_vp, C.POINTER(_f)],
     "pcnn_comm_unique_id": [_vp, C.POINTER(_sz)],
     "pcnn_comm_init_rank": [_vp, _vp, _i, _i],
     "pcnn_comm_destroy": [_vp],

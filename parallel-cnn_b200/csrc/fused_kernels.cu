@@ -364,11 +364,11 @@ struct ReduceArgs {
     float *grads;               // [NPACK] out
     float *params;              // [NPACK] in/out (when update)
     double *err_total;          // running error-norm sum
-    float *step_err;            // optional: where to store this step's error sum
+    float *step_err;            // optional ring of per-step error sums, indexed by *step_idx
+    const int *step_idx;
     const long long *cursor_in; // cursor mode: read to compute the effective global batch
-    long long *cursor_out;      // cursor mode: advanced by B * world (wrapping) when update
     long long n_total;
-    int B, world;
+    int B, world, rank_local;
     float dt;
     int update;                 // 1: apply update here (single GPU); 0: leave grads for the all-reduce
 };
@@ -380,11 +380,19 @@ __device__ __forceinline__ void apply_entry(float *params, int p, float g, float
     else params[p] += step * g;
 }
 
-__device__ __forceinline__ long long effective_global_batch(const long long *cursor, long long n_total, int B, int world) {
+// rank_local == 0: all ranks index one shared split (rank r starts at cursor + r * B), the global batch is clamped at
+// the end of the split.  rank_local == 1: every rank walks its OWN equally sized shard (pcnn_learn_host), so the
+// per-rank batch is clamped and multiplied by world.
+__device__ __forceinline__ long long effective_global_batch(const long long *cursor, long long n_total, int B, int world,
+                                                            int rank_local) {
     long long gb = (long long)B * world;
     if (cursor) {
         long long left = n_total - *cursor;
-        if (left < gb) gb = left;
+        if (rank_local) {
+            if (left < B) gb = left * world;
+        } else if (left < gb) {
+            gb = left;
+        }
     }
     return gb < 1 ? 1 : gb;
 }
@@ -405,21 +413,22 @@ __global__ void __launch_bounds__(256) k_reduce_slots(const ReduceArgs a) {
         a.grads[p] = g;
         if (a.update) {
             if (p < NPARAM) {
-                const float step = a.dt / (float)effective_global_batch(a.cursor_in, a.n_total, a.B, a.world);
+                const float step = a.dt / (float)effective_global_batch(a.cursor_in, a.n_total, a.B, a.world, a.rank_local);
                 apply_entry(a.params, p, g, step);
             } else {
                 *a.err_total += (double)g;
-                if (a.step_err) *a.step_err = g;
+                if (a.step_err) a.step_err[*a.step_idx & (STEP_ERR_CAP - 1)] = g;
             }
         }
     }
 }
 
 // cursor advance must not race with the reads above -> its own tiny kernel at the end of the step
-__global__ void k_advance_cursor(long long *cursor, long long n_total, long long stride) {
+__global__ void k_advance_cursor(long long *cursor, long long n_total, long long stride, int *step_idx) {
     long long c = *cursor + stride;
     if (c >= n_total) c = 0;
     *cursor = c;
+    *step_idx += 1;
 }
 
 // update after an all-reduce (grads already hold the global sum)
@@ -428,9 +437,10 @@ struct UpdateArgs {
     float *params;
     double *err_total;
     float *step_err;
+    const int *step_idx;
     const long long *cursor_in;
     long long n_total;
-    int B, world;
+    int B, world, rank_local;
     float dt;
 };
 __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
@@ -438,11 +448,11 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     if (p >= NPACK) return;
     const float g = a.grads[p];
     if (p < NPARAM) {
-        const float step = a.dt / (float)effective_global_batch(a.cursor_in, a.n_total, a.B, a.world);
+        const float step = a.dt / (float)effective_global_batch(a.cursor_in, a.n_total, a.B, a.world, a.rank_local);
         apply_entry(a.params, p, g, step);
     } else {
         *a.err_total += (double)g;
-        if (a.step_err) *a.step_err = g;
+        if (a.step_err) a.step_err[*a.step_idx & (STEP_ERR_CAP - 1)] = g;
     }
 }
 
@@ -481,38 +491,37 @@ int pcnn_fused_configure() {
     return PCNN_OK;
 }
 
-int pcnn_launch_fused_grad(pcnn_ctx *ctx, const void *images, int pixel_type, const uint8_t *labels, long n_total,
-                           long first, int B, bool use_cursor, int *grid_out) {
+int pcnn_launch_fused_grad(pcnn_ctx *ctx, const pcnn_step_src &src, int B, int *grid_out) {
     FusedArgs a{};
-    a.images = images;
-    a.labels = labels;
+    a.images = src.images;
+    a.labels = src.labels;
     a.params = ctx->d_params;
     a.slots = ctx->d_slots;
-    a.cursor = use_cursor ? ctx->d_cursor : nullptr;
-    a.first = first;
-    a.n_total = n_total;
+    a.cursor = src.use_cursor ? ctx->d_cursor : nullptr;
+    a.first = src.first;
+    a.n_total = src.n_total;
     a.B = B;
-    a.rank = use_cursor ? ctx->rank : 0;
+    a.rank = (src.use_cursor && !src.rank_local) ? ctx->rank : 0;
     a.world = ctx->world;
     int grid = fused_grid(ctx, B);
     if (grid_out) *grid_out = grid;
-    return launch_fused<true>(ctx, a, pixel_type, grid);
+    return launch_fused<true>(ctx, a, src.pixel_type, grid);
 }
 
-int pcnn_launch_reduce(pcnn_ctx *ctx, int grid_slots, int B, bool use_cursor, long n_total, bool update,
-                       float *step_err_out) {
+int pcnn_launch_reduce(pcnn_ctx *ctx, int grid_slots, int B, const pcnn_step_src &src, bool update, bool record_err) {
     ReduceArgs r{};
     r.slots = ctx->d_slots;
     r.nslots = grid_slots;
     r.grads = ctx->d_grads;
     r.params = ctx->d_params;
     r.err_total = ctx->d_err_total;
-    r.step_err = step_err_out;
-    r.cursor_in = use_cursor ? ctx->d_cursor : nullptr;
-    r.cursor_out = nullptr;
-    r.n_total = n_total;
+    r.step_err = record_err ? ctx->d_step_err : nullptr;
+    r.step_idx = ctx->d_step_idx;
+    r.cursor_in = src.use_cursor ? ctx->d_cursor : nullptr;
+    r.n_total = src.n_total;
     r.B = B;
     r.world = ctx->world;
+    r.rank_local = src.rank_local ? 1 : 0;
     r.dt = ctx->lr;
     r.update = update ? 1 : 0;
     k_reduce_slots<<<(NPACK + 31) / 32, 256, 0, ctx->stream>>>(r);
@@ -520,41 +529,66 @@ int pcnn_launch_reduce(pcnn_ctx *ctx, int grid_slots, int B, bool use_cursor, lo
     return PCNN_OK;
 }
 
-int pcnn_launch_update(pcnn_ctx *ctx, int B, bool use_cursor, long n_total) {
+int pcnn_launch_update(pcnn_ctx *ctx, int B, const pcnn_step_src &src, bool record_err) {
     UpdateArgs u{};
     u.grads = ctx->d_grads;
     u.params = ctx->d_params;
     u.err_total = ctx->d_err_total;
-    u.step_err = nullptr;
-    u.cursor_in = use_cursor ? ctx->d_cursor : nullptr;
-    u.n_total = n_total;
+    u.step_err = record_err ? ctx->d_step_err : nullptr;
+    u.step_idx = ctx->d_step_idx;
+    u.cursor_in = src.use_cursor ? ctx->d_cursor : nullptr;
+    u.n_total = src.n_total;
     u.B = B;
     u.world = ctx->world;
+    u.rank_local = src.rank_local ? 1 : 0;
     u.dt = ctx->lr;
     k_update<<<(NPACK + 255) / 256, 256, 0, ctx->stream>>>(u);
     PCNN_CHECK_LAUNCH(ctx);
     return PCNN_OK;
 }
 
-static int launch_advance(pcnn_ctx *ctx, long n_total, int B) {
-    k_advance_cursor<<<1, 1, 0, ctx->stream>>>(ctx->d_cursor, n_total, (long long)B * ctx->world);
+static int launch_advance(pcnn_ctx *ctx, const pcnn_step_src &src, int B) {
+    const long long stride = src.rank_local ? (long long)B : (long long)B * ctx->world;
+    k_advance_cursor<<<1, 1, 0, ctx->stream>>>(ctx->d_cursor, src.n_total, stride, ctx->d_step_idx);
     PCNN_CHECK_LAUNCH(ctx);
     return PCNN_OK;
 }
 
 // one full step on the context's stream: gradient kernel, slot reduction, [all-reduce + update], [cursor advance]
-static int enqueue_step(pcnn_ctx *ctx, const void *images, int pixel_type, const uint8_t *labels, long n_total,
-                        long first, int B, bool use_cursor, float *step_err_out) {
+static int enqueue_step(pcnn_ctx *ctx, const pcnn_step_src &src, int B) {
     int grid = 0, rc;
-    if ((rc = pcnn_launch_fused_grad(ctx, images, pixel_type, labels, n_total, first, B, use_cursor, &grid))) return rc;
+    if ((rc = pcnn_launch_fused_grad(ctx, src, B, &grid))) return rc;
     const bool distributed = ctx->world > 1 && ctx->nccl_comm;
-    if ((rc = pcnn_launch_reduce(ctx, grid, B, use_cursor, n_total, !distributed, step_err_out))) return rc;
+    if ((rc = pcnn_launch_reduce(ctx, grid, B, src, !distributed, src.use_cursor && !distributed))) return rc;
     if (distributed) {
         if ((rc = pcnn_comm_allreduce_packed(ctx))) return rc;
-        if ((rc = pcnn_launch_update(ctx, B, use_cursor, n_total))) return rc;
+        if ((rc = pcnn_launch_update(ctx, B, src, src.use_cursor))) return rc;
     }
-    if (use_cursor && (rc = launch_advance(ctx, n_total, B))) return rc;
+    if (src.use_cursor && (rc = launch_advance(ctx, src, B))) return rc;
     return PCNN_OK;
+}
+
+static pcnn_step_src src_of(const pcnn_split_binding &s, long first, bool use_cursor) {
+    pcnn_step_src r;
+    r.images = s.images;
+    r.labels = s.labels;
+    r.pixel_type = s.pixel_type;
+    r.n_total = s.n;
+    r.first = first;
+    r.use_cursor = use_cursor;
+    r.rank_local = s.rank_local;
+    return r;
+}
+static pcnn_step_src src_of_buffers(const void *images, int pixel_type, const uint8_t *labels, int B) {
+    pcnn_step_src r;
+    r.images = images;
+    r.labels = labels;
+    r.pixel_type = pixel_type;
+    r.n_total = B;
+    r.first = 0;
+    r.use_cursor = false;
+    r.rank_local = true;
+    return r;
 }
 
 static int check_batch_args(pcnn_ctx *ctx, const char *fn, const void *images, int pixel_type, const uint8_t *labels, int B) {
@@ -572,16 +606,16 @@ extern "C" int pcnn_compute_grads(pcnn_ctx *ctx, const void *dev_images, int pix
     if (rc) return rc;
     pcnn_device_guard g(ctx->device);
     int grid = 0;
-    if ((rc = pcnn_launch_fused_grad(ctx, dev_images, pixel_type, dev_labels, B, 0, B, false, &grid))) return rc;
-    // reduce without update; err_total untouched
-    return pcnn_launch_reduce(ctx, grid, B, false, B, false, nullptr);
+    const pcnn_step_src src = src_of_buffers(dev_images, pixel_type, dev_labels, B);
+    if ((rc = pcnn_launch_fused_grad(ctx, src, B, &grid))) return rc;
+    return pcnn_launch_reduce(ctx, grid, B, src, false, false);   // reduce only: no update, err_total untouched
 }
 
 extern "C" int pcnn_train_step_dev(pcnn_ctx *ctx, const void *dev_images, int pixel_type, const uint8_t *dev_labels, int B) {
     int rc = check_batch_args(ctx, "pcnn_train_step_dev", dev_images, pixel_type, dev_labels, B);
     if (rc) return rc;
     pcnn_device_guard g(ctx->device);
-    return enqueue_step(ctx, dev_images, pixel_type, dev_labels, B, 0, B, false, nullptr);
+    return enqueue_step(ctx, src_of_buffers(dev_images, pixel_type, dev_labels, B), B);
 }
 
 extern "C" int pcnn_train_step(pcnn_ctx *ctx, long first, int B) {
@@ -591,40 +625,55 @@ extern "C" int pcnn_train_step(pcnn_ctx *ctx, long first, int B) {
     PCNN_REQUIRE(B > 0 && first >= 0 && first + (long)B <= s.n, PCNN_ERR_ARG,
                  "pcnn_train_step: samples [%ld, %ld) outside the split of %ld", first, first + (long)B, s.n);
     pcnn_device_guard g(ctx->device);
-    return enqueue_step(ctx, s.images, s.pixel_type, s.labels, s.n, first, B, false, nullptr);
+    return enqueue_step(ctx, src_of(s, first, false), B);
 }
 
-// nsteps consecutive cursor-driven steps, captured once per (B, nsteps, split) into a CUDA graph and replayed
-static int run_cursor_steps(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, int nsteps) {
-    pcnn_graph_key key{B, nsteps, ctx->world, s.pixel_type, s.images, s.n};
+// Cursor-driven steps are replayed from CUDA graphs.  A run of nsteps is decomposed into graphs of 1024 / 256 / 64 /
+// 16 / 4 / 1 steps; the sample position and the step-error slot come from device-side counters, so one graph per
+// (size, B, split) serves any position.
+static const int GRAPH_SIZES[] = {1024, 256, 64, 16, 4, 1};
+
+static int get_step_graph(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, int nsteps, cudaGraphExec_t *out) {
+    pcnn_graph_key key{B, nsteps, ctx->world, s.pixel_type, s.rank_local ? 1 : 0, s.images, s.n};
     auto it = ctx->graphs.find(key);
+    if (it != ctx->graphs.end()) { *out = it->second; return PCNN_OK; }
+    cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
-    if (it == ctx->graphs.end()) {
-        cudaGraph_t graph = nullptr;
-        PCNN_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = PCNN_OK;
-        long before = ctx->launches;
-        for (int k = 0; k < nsteps && rc == PCNN_OK; ++k)
-            rc = enqueue_step(ctx, s.images, s.pixel_type, s.labels, s.n, 0, B, true, nullptr);
-        cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
-        ctx->launches = before;   // captured, not launched
-        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (e != cudaSuccess) return pcnn_fail_cuda(e, "cudaStreamEndCapture", __FILE__, __LINE__);
-        e = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e != cudaSuccess) return pcnn_fail_cuda(e, "cudaGraphInstantiate", __FILE__, __LINE__);
-        ctx->graphs[key] = exec;
-    } else {
-        exec = it->second;
-    }
-    PCNN_CUDA(cudaGraphLaunch(exec, ctx->stream));
+    PCNN_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = PCNN_OK;
+    const long before = ctx->launches;
+    const pcnn_step_src src = src_of(s, 0, true);
+    for (int k = 0; k < nsteps && rc == PCNN_OK; ++k) rc = enqueue_step(ctx, src, B);
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    ctx->launches = before;   // captured, not launched
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return pcnn_fail_cuda(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return pcnn_fail_cuda(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+    ctx->graphs[key] = exec;
+    *out = exec;
+    return PCNN_OK;
+}
+
+static int run_cursor_steps(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nsteps, bool launch) {
     const bool distributed = ctx->world > 1 && ctx->nccl_comm;
-    ctx->launches += (long)nsteps * (distributed ? 4 : 3);   // our kernels per step (the NCCL kernel is not ours)
+    for (int size : GRAPH_SIZES) {
+        while (nsteps >= size) {
+            cudaGraphExec_t exec = nullptr;
+            int rc = get_step_graph(ctx, s, B, size, &exec);
+            if (rc) return rc;
+            if (!launch) { nsteps %= size; break; }     // prepare mode: instantiate each size once
+            PCNN_CUDA(cudaGraphLaunch(exec, ctx->stream));
+            ctx->launches += (long)size * (distributed ? 4 : 3);   // our kernels per step (the NCCL kernel is not ours)
+            nsteps -= size;
+        }
+    }
     return PCNN_OK;
 }
 
 static int set_cursor(pcnn_ctx *ctx, long long v) {
-    // pinned scratch so the async copy is truly asynchronous; the value is consumed before h_scalar is reused
+    // pinned scratch so the copy is asynchronous; synchronise first so h_scalar is not overwritten while in flight
     PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
     *reinterpret_cast<long long *>(ctx->h_scalar) = v;
     PCNN_CUDA(cudaMemcpyAsync(ctx->d_cursor, ctx->h_scalar, sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
@@ -635,11 +684,20 @@ extern "C" int pcnn_train_steps(pcnn_ctx *ctx, long first, int B, int nsteps) {
     PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_train_steps: ctx is NULL");
     const pcnn_split_binding &s = ctx->split[PCNN_TRAIN_SET];
     PCNN_REQUIRE(s.n > 0, PCNN_ERR_STATE, "pcnn_train_steps: no training split bound");
-    PCNN_REQUIRE(B > 0 && nsteps > 0 && first >= 0 && first < s.n, PCNN_ERR_ARG, "pcnn_train_steps: bad arguments");
+    PCNN_REQUIRE(B > 0 && nsteps > 0 && first >= -1 && first < s.n, PCNN_ERR_ARG, "pcnn_train_steps: bad arguments");
     pcnn_device_guard g(ctx->device);
     int rc;
-    if (first >= 0 && (rc = set_cursor(ctx, first))) return rc;
-    return run_cursor_steps(ctx, s, B, nsteps);
+    if (first >= 0 && (rc = set_cursor(ctx, first))) return rc;     // first == -1: continue at the device cursor
+    return run_cursor_steps(ctx, s, B, nsteps, true);
+}
+
+extern "C" int pcnn_train_steps_prepare(pcnn_ctx *ctx, int B, int nsteps) {
+    PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_train_steps_prepare: ctx is NULL");
+    const pcnn_split_binding &s = ctx->split[PCNN_TRAIN_SET];
+    PCNN_REQUIRE(s.n > 0, PCNN_ERR_STATE, "pcnn_train_steps_prepare: no training split bound");
+    PCNN_REQUIRE(B > 0 && nsteps > 0, PCNN_ERR_ARG, "pcnn_train_steps_prepare: bad arguments");
+    pcnn_device_guard g(ctx->device);
+    return run_cursor_steps(ctx, s, B, nsteps, false);
 }
 
 extern "C" int pcnn_learn(pcnn_ctx *ctx, int B, int epochs, float *mean_err_out) {
@@ -650,19 +708,12 @@ extern "C" int pcnn_learn(pcnn_ctx *ctx, int B, int epochs, float *mean_err_out)
     pcnn_device_guard g(ctx->device);
     const long gb = (long)B * ctx->world;
     const long steps_per_epoch = (s.n + gb - 1) / gb;
-    // replay graphs of at most CHUNK steps; the device-side cursor makes every chunk position-independent
-    const long CHUNK = 500;
     int rc;
     double err = 0.0;
     for (int ep = 0; ep < epochs; ++ep) {
         if ((rc = set_cursor(ctx, 0))) return rc;
         if ((rc = pcnn_err_sum(ctx, nullptr, 1))) return rc;
-        long left = steps_per_epoch;
-        while (left > 0) {
-            int k = (int)(left < CHUNK ? left : CHUNK);
-            if ((rc = run_cursor_steps(ctx, s, B, k))) return rc;
-            left -= k;
-        }
+        if ((rc = run_cursor_steps(ctx, s, B, steps_per_epoch, true))) return rc;
         if ((rc = pcnn_err_sum(ctx, &err, 0))) return rc;
     }
     if (mean_err_out) *mean_err_out = (float)(err / (double)s.n);
@@ -702,7 +753,7 @@ extern "C" int pcnn_train_step_host(pcnn_ctx *ctx, const void *host_images, int 
     // (cudaHostRegister'ed or cudaMallocHost'ed by the caller) goes by DMA directly
     PCNN_CUDA(cudaMemcpyAsync(ctx->d_stage[0], host_images, ib, cudaMemcpyHostToDevice, ctx->stream));
     PCNN_CUDA(cudaMemcpyAsync(ctx->d_stage_lab[0], host_labels, (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
-    if ((rc = enqueue_step(ctx, ctx->d_stage[0], pixel_type, ctx->d_stage_lab[0], B, 0, B, false, nullptr))) return rc;
+    if ((rc = enqueue_step(ctx, src_of_buffers(ctx->d_stage[0], pixel_type, ctx->d_stage_lab[0], B), B))) return rc;
     // the step's error sum is element OFF_ERR of the packed gradient (all-reduced when distributed)
     PCNN_CUDA(cudaMemcpyAsync(ctx->h_scalar, ctx->d_grads + OFF_ERR, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -717,19 +768,30 @@ extern "C" int pcnn_learn_host(pcnn_ctx *ctx, const void *host_images, int pixel
     PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_learn_host: ctx is NULL");
     PCNN_REQUIRE(host_images && host_labels && n > 0 && B > 0 && epochs > 0, PCNN_ERR_ARG, "pcnn_learn_host: bad arguments");
     PCNN_REQUIRE(pixel_type == PCNN_U8 || pixel_type == PCNN_F32, PCNN_ERR_ARG, "pcnn_learn_host: bad pixel type");
-    PCNN_REQUIRE(ctx->world == 1, PCNN_ERR_STATE, "pcnn_learn_host: single-GPU entry point (shard on the host for data parallel runs)");
     pcnn_device_guard g(ctx->device);
     const size_t px = (pixel_type == PCNN_F32 ? 4 : 1);
     long chunk_samples = ((long)(4 << 20) / (long)(PCNN_IMG * px));            // ~4 MiB per chunk
     chunk_samples = (chunk_samples / B) * B;
     if (chunk_samples < B) chunk_samples = B;
+    if (chunk_samples / B > STEP_ERR_CAP) chunk_samples = (long)STEP_ERR_CAP * B;
+    // data parallel: `host_images` is THIS rank's shard (all ranks must pass equally sized shards); every step
+    // all-reduces the packed gradient and divides the step by B * world
     int rc;
     if ((rc = ensure_stage(ctx, chunk_samples))) return rc;
     const char *hi = reinterpret_cast<const char *>(host_images);
     double err = 0.0;
+    const long total_steps = (n + B - 1) / B;
+    if (total_steps > ctx->h_step_err_cap) {
+        PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_step_err) cudaFreeHost(ctx->h_step_err);
+        ctx->h_step_err = nullptr;
+        PCNN_CUDA(cudaMallocHost((void **)&ctx->h_step_err, (size_t)total_steps * sizeof(float)));
+        ctx->h_step_err_cap = total_steps;
+    }
     for (int ep = 0; ep < epochs; ++ep) {
         if ((rc = pcnn_err_sum(ctx, nullptr, 1))) return rc;
         int slot = 0;
+        long steps_done = 0;
         for (long off = 0; off < n; off += chunk_samples, slot ^= 1) {
             const long cs = (n - off < chunk_samples) ? n - off : chunk_samples;
             // wait until the compute stream has finished with this staging buffer, then copy into it
@@ -745,14 +807,21 @@ extern "C" int pcnn_learn_host(pcnn_ctx *ctx, const void *host_images, int pixel
             tmp.labels = ctx->d_stage_lab[slot];
             tmp.pixel_type = pixel_type;
             tmp.n = cs;
+            tmp.rank_local = true;
             PCNN_CUDA(cudaMemsetAsync(ctx->d_cursor, 0, sizeof(long long), ctx->stream));
+            PCNN_CUDA(cudaMemsetAsync(ctx->d_step_idx, 0, sizeof(int), ctx->stream));
             const int steps = (int)((cs + B - 1) / B);
-            if ((rc = run_cursor_steps(ctx, tmp, B, steps))) return rc;
+            if ((rc = run_cursor_steps(ctx, tmp, B, steps, true))) return rc;
+            // every step's result (its error-norm sum) goes back to the host
+            PCNN_CUDA(cudaMemcpyAsync(ctx->h_step_err + steps_done, ctx->d_step_err, (size_t)steps * sizeof(float),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+            steps_done += steps;
             PCNN_CUDA(cudaEventRecord(ctx->ev_done[slot], ctx->stream));
         }
         if ((rc = pcnn_err_sum(ctx, &err, 0))) return rc;     // blocking read-back of the epoch's error sum
+        ctx->step_err_count = steps_done;
     }
-    if (mean_err_out) *mean_err_out = (float)(err / (double)n);
+    if (mean_err_out) *mean_err_out = (float)(err / ((double)n * ctx->world));   // err is the all-reduced sum
     return PCNN_OK;
 }
 
@@ -797,5 +866,83 @@ extern "C" int pcnn_test(pcnn_ctx *ctx, long *wrong_out) {
     PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
     wrong = *reinterpret_cast<int *>(ctx->h_scalar);
     *wrong_out = wrong;
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_step_errs(pcnn_ctx *ctx, float *host_out, long cap, long *count_out) {
+    PCNN_REQUIRE(ctx && count_out, PCNN_ERR_ARG, "pcnn_step_errs: NULL argument");
+    pcnn_device_guard g(ctx->device);
+    PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    *count_out = ctx->step_err_count;
+    if (host_out)
+        for (long i = 0; i < ctx->step_err_count && i < cap; ++i) host_out[i] = ctx->h_step_err[i];
+    return PCNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ measurement helpers
+extern "C" int pcnn_time_fused_kernel(pcnn_ctx *ctx, int B, int iters, float *avg_ms_out) {
+    PCNN_REQUIRE(ctx && avg_ms_out, PCNN_ERR_ARG, "pcnn_time_fused_kernel: NULL argument");
+    const pcnn_split_binding &s = ctx->split[PCNN_TRAIN_SET];
+    PCNN_REQUIRE(s.n >= B && B > 0 && iters > 0, PCNN_ERR_STATE, "pcnn_time_fused_kernel: bind a train split of at least B samples");
+    pcnn_device_guard g(ctx->device);
+    cudaEvent_t e0, e1;
+    PCNN_CUDA(cudaEventCreate(&e0));
+    PCNN_CUDA(cudaEventCreate(&e1));
+    const long windows = s.n / B;
+    int rc = PCNN_OK, grid = 0;
+    long w = 0;
+    for (int i = 0; i < iters / 10 + 3 && rc == PCNN_OK; ++i, w = (w + 1) % windows)
+        rc = pcnn_launch_fused_grad(ctx, src_of(s, w * B, false), B, &grid);
+    if (rc == PCNN_OK) {
+        cudaEventRecord(e0, ctx->stream);
+        for (int i = 0; i < iters && rc == PCNN_OK; ++i, w = (w + 1) % windows)
+            rc = pcnn_launch_fused_grad(ctx, src_of(s, w * B, false), B, &grid);
+        cudaEventRecord(e1, ctx->stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e != cudaSuccess) rc = pcnn_fail_cuda(e, "event timing", __FILE__, __LINE__);
+        *avg_ms_out = ms / (float)iters;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+namespace {
+// 8 independent FMA chains per thread, 4096 iterations: 65,536 FMAs per thread, no memory traffic
+__global__ void __launch_bounds__(256) k_fma_peak(float *out, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+    for (int i = 0; i < 4096; ++i) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    if (x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7 == 12345.678f) out[0] = x0;
+}
+}  // namespace
+
+extern "C" int pcnn_measure_fp32_peak(pcnn_ctx *ctx, float *tflops_out) {
+    PCNN_REQUIRE(ctx && tflops_out, PCNN_ERR_ARG, "pcnn_measure_fp32_peak: NULL argument");
+    pcnn_device_guard g(ctx->device);
+    cudaEvent_t e0, e1;
+    PCNN_CUDA(cudaEventCreate(&e0));
+    PCNN_CUDA(cudaEventCreate(&e1));
+    const int grid = ctx->sm_count * 8, reps = 20;
+    for (int i = 0; i < 3; ++i) k_fma_peak<<<grid, 256, 0, ctx->stream>>>(ctx->d_grads, 0.999f, 0.001f);
+    cudaEventRecord(e0, ctx->stream);
+    for (int i = 0; i < reps; ++i) k_fma_peak<<<grid, 256, 0, ctx->stream>>>(ctx->d_grads, 0.999f, 0.001f);
+    cudaEventRecord(e1, ctx->stream);
+    ctx->launches += reps + 3;
+    PCNN_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    PCNN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = 2.0 * 16.0 * 4096.0 * 256.0 * grid * reps;
+    *tflops_out = (float)(flops / (ms * 1e-3) / 1e12);
     return PCNN_OK;
 }

@@ -69,6 +69,10 @@ extern "C" int pcnn_create(pcnn_ctx **out, int device, void *stream) {
     PCNN_CUDA(cudaMalloc(&c->d_err_total, sizeof(double)));
     PCNN_CUDA(cudaMalloc(&c->d_cursor, sizeof(long long)));
     PCNN_CUDA(cudaMalloc(&c->d_wrong, sizeof(int)));
+    PCNN_CUDA(cudaMalloc(&c->d_step_err, STEP_ERR_CAP * sizeof(float)));
+    PCNN_CUDA(cudaMemset(c->d_step_err, 0, STEP_ERR_CAP * sizeof(float)));
+    PCNN_CUDA(cudaMalloc(&c->d_step_idx, sizeof(int)));
+    PCNN_CUDA(cudaMemset(c->d_step_idx, 0, sizeof(int)));
     PCNN_CUDA(cudaMemset(c->d_params, 0, NPACK * sizeof(float)));
     PCNN_CUDA(cudaMemset(c->d_grads, 0, NPACK * sizeof(float)));
     PCNN_CUDA(cudaMemset(c->d_err_total, 0, sizeof(double)));
@@ -118,6 +122,8 @@ extern "C" int pcnn_destroy(pcnn_ctx *ctx) {
     cudaFree(ctx->d_cursor);
     cudaFree(ctx->d_wrong);
     if (ctx->d_step_err) cudaFree(ctx->d_step_err);
+    if (ctx->d_step_idx) cudaFree(ctx->d_step_idx);
+    if (ctx->h_step_err) cudaFreeHost(ctx->h_step_err);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -21,6 +21,7 @@ constexpr int OFF_C1W = PCNN_OFF_C1W, OFF_C1B = PCNN_OFF_C1B, OFF_S1W = PCNN_OFF
 constexpr int FUSED_THREADS = 224;          // 216 workers (one per (map, 4x4 window)) + 8 helpers
 constexpr int FUSED_WORKERS = 216;
 constexpr int FUSED_CTAS_PER_SM = 2;
+constexpr int STEP_ERR_CAP = 4096;         // most steps one replayed graph may hold
 constexpr int MAX_SLOTS = 148 * 4;          // upper bound on the fused grid (per-CTA partial-gradient slots)
 
 struct pcnn_split_binding {
@@ -30,15 +31,27 @@ struct pcnn_split_binding {
     long n = 0;
     void *owned_images = nullptr;           // non-null when uploaded through pcnn_dataset_upload
     void *owned_labels = nullptr;
+    bool rank_local = false;                // true: this rank's private shard (no rank offset into it)
+};
+
+// where one step takes its samples from
+struct pcnn_step_src {
+    const void *images = nullptr;
+    const uint8_t *labels = nullptr;
+    int pixel_type = PCNN_U8;
+    long n_total = 0;
+    long first = 0;                         // explicit start when !use_cursor
+    bool use_cursor = false;                // start = device-side cursor (+ rank * B unless rank_local)
+    bool rank_local = false;
 };
 
 struct pcnn_graph_key {
-    int B, nsteps, world, pixel_type;
+    int B, nsteps, world, pixel_type, rank_local;
     const void *images;
     long n;
     bool operator<(const pcnn_graph_key &o) const {
-        return std::tie(B, nsteps, world, pixel_type, images, n) <
-               std::tie(o.B, o.nsteps, o.world, o.pixel_type, o.images, o.n);
+        return std::tie(B, nsteps, world, pixel_type, rank_local, images, n) <
+               std::tie(o.B, o.nsteps, o.world, o.pixel_type, o.rank_local, o.images, o.n);
     }
 };
 
@@ -56,8 +69,10 @@ struct pcnn_ctx {
     double *d_err_total = nullptr;          // running sum of error norms (double)
     long long *d_cursor = nullptr;          // next global sample index for cursor-driven steps
     int *d_wrong = nullptr;                 // misclassification counter of pcnn_test
-    float *d_step_err = nullptr;            // [step_err_cap] per-step error sums for pcnn_learn_host
-    long step_err_cap = 0;
+    float *d_step_err = nullptr;            // [STEP_ERR_CAP] ring of per-step error sums, indexed by *d_step_idx
+    int *d_step_idx = nullptr;              // device-side step counter (advanced by every cursor-driven step)
+    float *h_step_err = nullptr;            // pinned, per-step error sums of the last pcnn_learn_host epoch
+    long h_step_err_cap = 0, step_err_count = 0;
 
     pcnn_split_binding split[2];
 
@@ -110,10 +125,8 @@ struct pcnn_device_guard {
 // ---- internal launchers shared between translation units -------------------------------------------------
 // fused_kernels.cu
 int pcnn_fused_configure();
-int pcnn_launch_fused_grad(pcnn_ctx *ctx, const void *images, int pixel_type, const uint8_t *labels,
-                           long n_total, long first, int B, bool use_cursor, int *grid_out);
-int pcnn_launch_reduce(pcnn_ctx *ctx, int grid_slots, int B, bool use_cursor, long n_total, bool update,
-                       float *step_err_out);
-int pcnn_launch_update(pcnn_ctx *ctx, int B, bool use_cursor, long n_total);
+int pcnn_launch_fused_grad(pcnn_ctx *ctx, const pcnn_step_src &src, int B, int *grid_out);
+int pcnn_launch_reduce(pcnn_ctx *ctx, int grid_slots, int B, const pcnn_step_src &src, bool update, bool record_err);
+int pcnn_launch_update(pcnn_ctx *ctx, int B, const pcnn_step_src &src, bool record_err);
 // comm.cu
 int pcnn_comm_allreduce_packed(pcnn_ctx *ctx);

@@ -228,6 +228,9 @@ class Engine:
     def train_steps(self, first, B, nsteps):
         self._call("pcnn_train_steps", int(first), int(B), int(nsteps))
 
+    def train_steps_prepare(self, B, nsteps):
+        self._call("pcnn_train_steps_prepare", int(B), int(nsteps))
+
     def train_step_dev(self, images_dev, pixel_type, labels_dev, B):
         self._call("pcnn_train_step_dev", _p(images_dev), int(pixel_type), _p(labels_dev), int(B))
 
@@ -262,6 +265,23 @@ class Engine:
         w = C.c_long()
         self._call("pcnn_test", C.byref(w))
         return w.value
+
+    def step_errs(self):
+        n = C.c_long()
+        self._call("pcnn_step_errs", None, 0, C.byref(n))
+        out = np.empty(n.value, np.float32)
+        self._call("pcnn_step_errs", out.ctypes.data, n.value, C.byref(n))
+        return out
+
+    def time_fused_kernel(self, B, iters):
+        ms = C.c_float()
+        self._call("pcnn_time_fused_kernel", int(B), int(iters), C.byref(ms))
+        return ms.value
+
+    def measure_fp32_peak(self):
+        t = C.c_float()
+        self._call("pcnn_measure_fp32_peak", C.byref(t))
+        return t.value
 
     # ------------------------------------------------------------------ data parallel
     @staticmethod
