@@ -175,9 +175,15 @@ def run_ours(a):
     imgs, labs = synthetic(DATASET_IMAGES, 7)
     eng.dataset_upload(pkg.TRAIN_SET, imgs, labs)
     if world > 1:
-        uid = [pkg.Engine.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        eng.comm_init_rank(uid[0], rank, world)
+        if a.mode == "graph":        # per-step kernels in CUDA graphs + one ncclAllReduce of the packed gradient per step
+            uid = [pkg.Engine.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            eng.comm_init_rank(uid[0], rank, world)
+        else:                        # persistent kernel, gradient chunks exchanged in-kernel over NVLink peer memory
+            handles = [None] * world
+            dist.all_gather_object(handles, eng.p2p_export())
+            eng.p2p_attach(handles, rank, world)
+    eng.set_step_mode({"auto": pkg.MODE_AUTO, "graph": pkg.MODE_GRAPH, "persistent": pkg.MODE_PERSISTENT}[a.mode])
 
     def barrier():
         if world > 1:
@@ -265,6 +271,8 @@ def run_ours(a):
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": "lenet_mnist_train_fp32_fused_step (BASELINE.json configs[1])", "batch_per_gpu": B,
                        "global_batch": B * world, "pixel_type": "u8", "parallelism": f"dp{world}",
+                       "step_mode": ("graph+nccl" if world > 1 else "graph") if a.mode == "graph" else
+                                    ("persistent+nvlink_p2p" if world > 1 else "persistent"),
                        "l2": f"inputs larger than L2: steps walk a {DATASET_IMAGES}-image ({DATASET_IMAGES * 784 / 1e6:.0f} MB) device-resident set",
                        "update": "w += (dt / global_batch) * sum_b g_b, dt = 0.1 (equals the reference at batch 1)"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * 785 * world,
@@ -286,6 +294,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (BASELINE.json configs[1]: 256)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent"],
+                    help="auto/persistent: one cooperative kernel runs all K steps (N > 1: in-kernel NVLink exchange); "
+                         "graph: per-step kernels replayed from CUDA graphs (N > 1: ncclAllReduce per step)")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)

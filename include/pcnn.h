@@ -57,6 +57,8 @@ typedef enum {
     PCNN_ERR_NOGPU = -6   /* no CUDA device / not compute capability 10.x */
 } pcnn_status;
 
+#define PCNN_MAX_PEERS 8   /* GPUs of one NVSwitch domain the in-kernel gradient exchange addresses */
+typedef enum { PCNN_MODE_AUTO = 0, PCNN_MODE_GRAPH = 1, PCNN_MODE_PERSISTENT = 2 } pcnn_step_mode;
 typedef enum { PCNN_U8 = 0, PCNN_F32 = 1 } pcnn_pixel_type;   /* IDX bytes, or the reference's float[28][28] */
 typedef enum { PCNN_TRAIN_SET = 0, PCNN_TEST_SET = 1 } pcnn_split;
 
@@ -181,6 +183,18 @@ int pcnn_comm_unique_id(void *id_out, size_t *id_bytes);               /* rank 0
 int pcnn_comm_init_rank(pcnn_ctx *ctx, const void *id, int rank, int world);
 int pcnn_comm_destroy(pcnn_ctx *ctx);
 int pcnn_allreduce_grads(pcnn_ctx *ctx);
+/* In-kernel exchange over NVLink / NVSwitch peer memory (no NCCL launch per step): every rank exports one IPC handle
+ * (64 bytes) for its inbox, the handles of all ranks are gathered by any rendezvous and attached.  Afterwards the
+ * persistent training kernel pushes its chunk of the reduced gradient straight into every peer's inbox and adds the
+ * ranks' chunks in rank order, inside the step. */
+int pcnn_p2p_export(pcnn_ctx *ctx, void *handle_out, size_t *handle_bytes);
+int pcnn_p2p_attach(pcnn_ctx *ctx, const void *handles, int rank, int world);
+int pcnn_p2p_detach(pcnn_ctx *ctx);
+/* How cursor-driven steps (pcnn_train_steps, pcnn_learn, pcnn_learn_host) execute: PCNN_MODE_PERSISTENT = one
+ * cooperative kernel running all steps (grid barriers, in-kernel reduction/update/exchange); PCNN_MODE_GRAPH = CUDA
+ * graphs of per-step kernels (+ NCCL all-reduce when distributed); PCNN_MODE_AUTO (default) = persistent whenever it
+ * can serve the configuration (single GPU, or peers attached), else graph. */
+int pcnn_set_step_mode(pcnn_ctx *ctx, int mode);
 
 /* ------------------------------------------------------------------ north_star extension ops (parity unpinned by the reference)
  * max-pool k x k stride k over [C][H][W] planes with argmax cache (flat index i*k+j, first maximum wins) */

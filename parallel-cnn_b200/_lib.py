@@ -13,6 +13,7 @@ HEADER = os.path.join(ROOT, "include", "pcnn.h")
 NPARAM = 2343
 OFF = dict(c1w=(0, 150), c1b=(150, 156), s1w=(156, 172), s1b=(172, 173), fw=(173, 2333), fb=(2333, 2343))
 U8, F32 = 0, 1
+MODE_AUTO, MODE_GRAPH, MODE_PERSISTENT = 0, 1, 2
 TRAIN_SET, TEST_SET = 0, 1
 
 
@@ -92,6 +93,10 @@ _SIG = {
     "pcnn_comm_init_rank": [_vp, _vp, _i, _i],
     "pcnn_comm_destroy": [_vp],
     "pcnn_allreduce_grads": [_vp],
+    "pcnn_p2p_export": [_vp, _vp, C.POINTER(_sz)],
+    "pcnn_p2p_attach": [_vp, _vp, _i, _i],
+    "pcnn_p2p_detach": [_vp],
+    "pcnn_set_step_mode": [_vp, _i],
     "pcnn_maxpool_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
     "pcnn_maxpool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
     "pcnn_softmax_ce": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp],

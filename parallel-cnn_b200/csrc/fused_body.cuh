@@ -1,0 +1,365 @@
+// parallel-cnn_b200/csrc/fused_body.cuh -- device code shared by the fused kernels: the per-image forward/backward
+// pass of one CTA and the CTA-level reduction of its register accumulators.  See fused_kernels.cu for the design notes.
+#pragma once
+#include "pcnn_internal.h"
+
+namespace pcnn_fused {
+
+constexpr int NT = FUSED_THREADS;
+constexpr int NWK = FUSED_WORKERS;
+constexpr int NWARP = NT / 32;          // 7
+constexpr int RED_STRIDE = 27;          // 25 c1 taps + c1 bias sum, padded to an odd stride
+
+template <typename InT> struct FusedSmem {
+    alignas(16) float params[NPACK];                 // packed parameters (9,376 B)
+    alignas(16) float imgf[2][PCNN_IMG];             // fp32 image, double buffered
+    alignas(16) InT stage[2][PCNN_IMG];              // raw staging target of the bulk copies (u8 path only)
+    alignas(16) float red[NWK * RED_STRIDE];         // epilogue scratch
+    float fc_red[NWARP][PCNN_F];
+    float red_s1[NWARP][17];
+    float dpre_f[PCNN_F];
+    float f_out[PCNN_F];
+    int label[2];
+    alignas(8) unsigned long long mbar[3];           // [0],[1]: image stages, [2]: parameters
+};
+
+// ---- mbarrier / bulk-copy helpers (PTX ISA: mbarrier, cp.async.bulk) -------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 1 / (1 + e^-v) = 1 / (1 + 2^(-v log2 e)): MUFU.EX2 + MUFU.RCP.  The exponent product is rounded to fp32, so the
+// relative error of e^-v grows like |v| * 6e-8 (|v| < 30 here); the sigmoid inherits at most (1 - sigma) of it.
+__device__ __forceinline__ float sigmoid_fast(float v) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    return __fdividef(1.0f, 1.0f + e);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// mnist.h:145 + Main.cpp:64: (float)((double)u / 255.0).  u / 255 has a period-8 binary expansion, so rounding the
+// exact quotient straight to fp32 equals rounding via double (checked for all 256 values in tests/).
+__device__ __forceinline__ float pixel_to_float(uint8_t u) { return __fdiv_rn((float)u, 255.0f); }
+
+struct ThreadId {
+    int t, warp, lane, m, wx, wy;
+    bool worker;
+    __device__ __forceinline__ ThreadId() {
+        t = threadIdx.x;
+        warp = t >> 5;
+        lane = t & 31;
+        worker = t < NWK;
+        m = worker ? t / 36 : 0;
+        wx = worker ? (t % 36) / 6 : 0;
+        wy = worker ? t % 6 : 0;
+    }
+};
+
+// register-resident accumulators of one thread, kept across all images a CTA processes in one step
+struct Acc {
+    float dw_c1[25], dw_s1[16], dw_f[PCNN_F];
+    float bsum_c1, bsum_s1, gfb, err_acc;
+    int wrong;
+    __device__ __forceinline__ void zero() {
+#pragma unroll
+        for (int i = 0; i < 25; ++i) dw_c1[i] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dw_s1[i] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < PCNN_F; ++i) dw_f[i] = 0.0f;
+        bsum_c1 = bsum_s1 = gfb = err_acc = 0.0f;
+        wrong = 0;
+    }
+};
+
+template <typename InT> __device__ __forceinline__ void init_barriers(FusedSmem<InT> &S) {
+    if (threadIdx.x == 0) {
+        mbar_init(&S.mbar[0], 1);
+        mbar_init(&S.mbar[1], 1);
+        mbar_init(&S.mbar[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// thread 0 only: start the bulk copy of one image into staging buffer `buf`
+template <typename InT> __device__ __forceinline__ void issue_image(FusedSmem<InT> &S, int buf, const InT *src) {
+    constexpr bool IS_U8 = (sizeof(InT) == 1);
+    constexpr unsigned IMG_BYTES = PCNN_IMG * sizeof(InT);
+    mbar_expect_tx(&S.mbar[buf], IMG_BYTES);
+    bulk_g2s(IS_U8 ? (void *)S.stage[buf] : (void *)S.imgf[buf], src, IMG_BYTES, &S.mbar[buf]);
+}
+// thread 0 only: start the bulk copy of the packed parameters
+template <typename InT> __device__ __forceinline__ void issue_params(FusedSmem<InT> &S, const float *params) {
+    mbar_expect_tx(&S.mbar[2], NPACK * 4);
+    bulk_g2s(S.params, params, NPACK * 4, &S.mbar[2]);
+}
+
+struct EvalOut {
+    float *f_out;     // this image's 10 outputs or null
+    uint8_t *pred;    // this image's prediction or null
+    bool has_label;
+};
+
+// One image through the CTA.  `li` is the CTA-local running image counter (selects the staging buffer and the mbarrier
+// phase); the image must have been issued into buffer li & 1.  `next_src` (or null) is prefetched into the other buffer
+// right after the first barrier.  `params_parity` < 0: parameters already resident; otherwise wait on mbar[2] with that
+// parity before the first use of S.params (lets the parameter copy overlap the u8 -> fp32 conversion).
+template <typename InT, bool TRAIN>
+__device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id, int li, const uint8_t *label_ptr,
+                                           const InT *next_src, int params_parity, Acc &A, const EvalOut &ev) {
+    constexpr bool IS_U8 = (sizeof(InT) == 1);
+    const int t = id.t, warp = id.warp, lane = id.lane;
+    const int buf = li & 1;
+    const unsigned parity = (li >> 1) & 1;
+    // ---- P0: the image has landed; convert to fp32 (u8 path), fetch the label
+    mbar_wait(&S.mbar[buf], parity);
+    if (IS_U8) {
+        if (t < 196) {
+            uchar4 q = reinterpret_cast<const uchar4 *>(S.stage[buf])[t];
+            float4 f = make_float4(pixel_to_float(q.x), pixel_to_float(q.y), pixel_to_float(q.z), pixel_to_float(q.w));
+            reinterpret_cast<float4 *>(S.imgf[buf])[t] = f;
+        }
+    }
+    if (t == NWK && label_ptr) S.label[buf] = (int)*label_ptr;
+    if (params_parity >= 0) mbar_wait(&S.mbar[2], (unsigned)params_parity);
+    __syncthreads();                                                         // sync #1
+    if (t == 0 && next_src) issue_image(S, buf ^ 1, next_src);
+
+    // ---- P1: c1 (5x5 valid conv, layer.h:105-140) + sigmoid, s1 (4x4/4 weighted sum, layer.h:143-181) + sigmoid
+    float o[16];         // this worker's 4x4 block of c1 outputs
+    float s1o = 0.0f;    // its s1 output
+    float fcp[PCNN_F];
+#pragma unroll
+    for (int q = 0; q < PCNN_F; ++q) fcp[q] = 0.0f;
+    if (id.worker) {
+        const float *ip = S.imgf[buf] + (4 * id.wx) * 28 + 4 * id.wy;
+        float in[8][8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
+            float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
+            in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = lo.z; in[r][3] = lo.w;
+            in[r][4] = hi.x; in[r][5] = hi.y; in[r][6] = hi.z; in[r][7] = hi.w;
+        }
+        float acc[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) acc[p] = 0.0f;
+        const float *wc = S.params + OFF_C1W + id.m * 25;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float w = wc[i * 5 + j];
+#pragma unroll
+                for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                    for (int oy = 0; oy < 4; ++oy) acc[ox * 4 + oy] = fmaf(in[ox + i][oy + j], w, acc[ox * 4 + oy]);
+            }
+        const float bc = S.params[OFF_C1B + id.m];
+        float s1pre = 0.0f;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            o[p] = sigmoid_fast(acc[p] + bc);
+            s1pre = fmaf(S.params[OFF_S1W + p], o[p], s1pre);
+        }
+        s1o = sigmoid_fast(s1pre + S.params[OFF_S1B]);
+        // fp_preact_f partial products (layer.h:184-203): this worker owns input k = t
+#pragma unroll
+        for (int q = 0; q < PCNN_F; ++q) fcp[q] = S.params[OFF_FW + q * PCNN_S1 + t] * s1o;
+    } else {
+#pragma unroll
+        for (int p = 0; p < 16; ++p) o[p] = 0.0f;
+    }
+#pragma unroll
+    for (int q = 0; q < PCNN_F; ++q) {
+        float v = warp_sum(fcp[q]);
+        if (lane == 0) S.fc_red[warp][q] = v;
+    }
+    __syncthreads();                                                         // sync #2
+
+    // ---- P2: f layer output, makeError (layer.h:91-95), vectorNorm (Main.cpp:28-34)
+    if (warp == 0) {
+        float d = 0.0f, outv = 0.0f;
+        if (lane < PCNN_F) {
+            float pre = 0.0f;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) pre += S.fc_red[w][lane];
+            pre += S.params[OFF_FB + lane];                                  // fp_bias_f, layer.h:206-211
+            outv = sigmoid_fast(pre);
+            if (TRAIN) {
+                const int y = S.label[buf];
+                d = (lane == y ? 1.0f : 0.0f) - outv;
+                S.dpre_f[lane] = d;
+                A.gfb += d;
+            } else {
+                S.f_out[lane] = outv;
+                if (ev.f_out) ev.f_out[lane] = outv;
+            }
+        }
+        if (TRAIN) {
+            float ss = warp_sum(d * d);
+            if (lane == 0) A.err_acc += sqrtf(ss);
+        } else {
+            __syncwarp();
+            if (lane == 0) {                                                 // classify(), Main.cpp:193-197
+                int best = 0;
+#pragma unroll
+                for (int q = 1; q < PCNN_F; ++q)
+                    if (S.f_out[best] < S.f_out[q]) best = q;
+                if (ev.pred) *ev.pred = (uint8_t)best;
+                if (ev.has_label && best != S.label[buf]) ++A.wrong;
+            }
+        }
+    }
+    if (!TRAIN) return;   // the next image's sync #1 orders the reuse of fc_red / f_out
+    __syncthreads();                                                         // sync #3
+
+    // ---- P3: backward chain (Main.cpp:114-131)
+    if (id.worker) {
+        float dout_s1 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < PCNN_F; ++q) {
+            const float dq = S.dpre_f[q];
+            A.dw_f[q] = fmaf(dq, s1o, A.dw_f[q]);                                          // bp_weight_f, layer.h:214-227
+            dout_s1 = fmaf(S.params[OFF_FW + q * PCNN_S1 + t], dq, dout_s1);                // bp_output_s1, layer.h:237-257
+        }
+        const float dpre_s1 = dout_s1 * s1o * (1.0f - s1o);                                // bp_preact_s1, layer.h:260-270
+        A.bsum_s1 += dpre_s1;                                                               // bp_bias_s1 accumulator, layer.h:303-314
+        float dpc[16];
+        float bs = 0.0f;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            A.dw_s1[p] = fmaf(dpre_s1, o[p], A.dw_s1[p]);                                   // bp_weight_s1, layer.h:272-300
+            const float dout_c1 = S.params[OFF_S1W + p] * dpre_s1;                          // bp_output_c1, layer.h:319-346
+            dpc[p] = dout_c1 * (o[p] * (1.0f - o[p]));                                      // bp_preact_c1, layer.h:348-369
+            bs += dpc[p];
+        }
+        A.bsum_c1 += bs;                                                                    // bp_bias_c1 accumulator, layer.h:400-410
+        // bp_weight_c1, layer.h:371-395 (the /576 is applied once in the epilogue)
+        const float *ip = S.imgf[buf] + (4 * id.wx) * 28 + 4 * id.wy;
+        float in[8][8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
+            float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
+            in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = lo.z; in[r][3] = lo.w;
+            in[r][4] = hi.x; in[r][5] = hi.y; in[r][6] = hi.z; in[r][7] = hi.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                float s = A.dw_c1[i * 5 + j];
+#pragma unroll
+                for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                    for (int oy = 0; oy < 4; ++oy) s = fmaf(dpc[ox * 4 + oy], in[ox + i][oy + j], s);
+                A.dw_c1[i * 5 + j] = s;
+            }
+    }
+}
+
+// Reduce the register accumulators of the 216 workers in a fixed order and write this CTA's packed partial gradient
+// (slot[NPACK]).  Ends with all of the CTA's global stores issued (callers fence as needed).
+template <typename InT>
+__device__ __forceinline__ void cta_epilogue(FusedSmem<InT> &S, const ThreadId &id, const Acc &A, float *slot) {
+    const int t = id.t, warp = id.warp, lane = id.lane;
+    __syncthreads();
+    if (id.worker) {
+#pragma unroll
+        for (int i = 0; i < 25; ++i) S.red[t * RED_STRIDE + i] = A.dw_c1[i];
+        S.red[t * RED_STRIDE + 25] = A.bsum_c1;
+#pragma unroll
+        for (int q = 0; q < PCNN_F; ++q) slot[OFF_FW + q * PCNN_S1 + t] = A.dw_f[q];   // column t is private to this worker
+    }
+#pragma unroll
+    for (int p = 0; p < 16; ++p) {
+        float v = warp_sum(A.dw_s1[p]);
+        if (lane == 0) S.red_s1[warp][p] = v;
+    }
+    {
+        float v = warp_sum(A.bsum_s1);
+        if (lane == 0) S.red_s1[warp][16] = v;
+    }
+    __syncthreads();
+    if (t < 156) {                       // 150 c1 taps + 6 c1 bias sums: sum over the 36 windows of a map, 4 chains
+        const int mm = t < 150 ? t / 25 : t - 150;
+        const int col = t < 150 ? t % 25 : 25;
+        const float *r = S.red + (mm * 36) * RED_STRIDE + col;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 36; w += 4) {
+            s0 += r[(w + 0) * RED_STRIDE];
+            s1 += r[(w + 1) * RED_STRIDE];
+            s2 += r[(w + 2) * RED_STRIDE];
+            s3 += r[(w + 3) * RED_STRIDE];
+        }
+        const float s = (s0 + s1) + (s2 + s3);
+        if (t < 150) slot[OFF_C1W + t] = s * (1.0f / 576.0f);
+        else slot[OFF_C1B + mm] = s;
+    } else if (t < 173) {                // s1 taps and s1 bias sum
+        const int p = t - 156;
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) s += S.red_s1[w][p];
+        slot[OFF_S1W + p] = s;           // p == 16 lands on OFF_S1B
+    }
+    if (t < PCNN_F) slot[OFF_FB + t] = A.gfb;
+    if (t == 0) slot[OFF_ERR] = A.err_acc;
+}
+
+// entry p of the packed vector: w += step * g in the reference's operand order (layer.h:99, :316, :412)
+__device__ __forceinline__ float updated_entry(float w, int p, float g, float step) {
+    if (p >= OFF_C1B && p < OFF_S1W) return w + step * g / 576.0f;
+    if (p == OFF_S1B) return w + step * g / 216.0f;
+    return w + step * g;
+}
+
+// rank_local == 0: all ranks index one shared split (rank r starts at cursor + r * B), the global batch is clamped at
+// the end of the split.  rank_local == 1: every rank walks its OWN equally sized shard (pcnn_learn_host), so the
+// per-rank batch is clamped and multiplied by world.
+__device__ __forceinline__ long long effective_global_batch(long long cursor, bool have_cursor, long long n_total, int B,
+                                                            int world, int rank_local) {
+    long long gb = (long long)B * world;
+    if (have_cursor) {
+        long long left = n_total - cursor;
+        if (rank_local) {
+            if (left < B) gb = left * world;
+        } else if (left < gb) {
+            gb = left;
+        }
+    }
+    return gb < 1 ? 1 : gb;
+}
+
+}  // namespace pcnn_fused

@@ -19,69 +19,11 @@
 //
 // Numerics: fp32 with FMA contraction and tree-ordered sums, float sigmoid 1/(1+expf(-v)); differs from the
 // reference's sequential un-fused sums and double exp by a few ulp per value (tolerances in tests/ and DESIGN.md).
-#include "pcnn_internal.h"
+#include "fused_body.cuh"
+
+using namespace pcnn_fused;
 
 namespace {
-
-constexpr int NT = FUSED_THREADS;
-constexpr int NWK = FUSED_WORKERS;
-constexpr int NWARP = NT / 32;          // 7
-constexpr int RED_STRIDE = 27;          // 25 c1 taps + c1 bias sum, padded to an odd stride
-
-template <typename InT> struct FusedSmem {
-    alignas(16) float params[NPACK];                 // packed parameters (9,376 B)
-    alignas(16) float imgf[2][PCNN_IMG];             // fp32 image, double buffered
-    alignas(16) InT stage[2][PCNN_IMG];              // raw staging target of the bulk copies (u8 path only)
-    alignas(16) float red[NWK * RED_STRIDE];         // epilogue scratch
-    float fc_red[NWARP][PCNN_F];
-    float red_s1[NWARP][17];
-    float dpre_f[PCNN_F];
-    float f_out[PCNN_F];
-    int label[2];
-    alignas(8) unsigned long long mbar[3];           // [0],[1]: image stages, [2]: parameters
-};
-
-// ---- mbarrier / bulk-copy helpers (PTX ISA: mbarrier, cp.async.bulk) -------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// 1 / (1 + e^-v): accurate expf (2 ulp), approximate reciprocal (1 ulp)
-__device__ __forceinline__ float sigmoid_fast(float v) { return __fdividef(1.0f, 1.0f + expf(-v)); }
-
-__device__ __forceinline__ float warp_sum(float v) {
-    v += __shfl_xor_sync(0xffffffffu, v, 16);
-    v += __shfl_xor_sync(0xffffffffu, v, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v;
-}
-
-// mnist.h:145 + Main.cpp:64: (float)((double)u / 255.0).  u / 255 has a period-8 binary expansion, so rounding the
-// exact quotient straight to fp32 equals rounding via double (checked for all 256 values in tests/).
-__device__ __forceinline__ float pixel_to_float(uint8_t u) { return __fdiv_rn((float)u, 255.0f); }
 
 struct FusedArgs {
     const void *images;          // [n_total][784] u8 or f32
@@ -102,259 +44,42 @@ template <typename InT, bool TRAIN>
 __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_fused(const FusedArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem<InT> &S = *reinterpret_cast<FusedSmem<InT> *>(smem_raw);
-    constexpr bool IS_U8 = (sizeof(InT) == 1);
-    constexpr unsigned IMG_BYTES = PCNN_IMG * sizeof(InT);
-
-    const int t = threadIdx.x;
-    const int warp = t >> 5, lane = t & 31;
-    const bool worker = t < NWK;
-    const int m = worker ? t / 36 : 0;
-    const int wx = worker ? (t % 36) / 6 : 0;
-    const int wy = worker ? t % 6 : 0;
+    const ThreadId id;
 
     // this rank's slice of the (global) batch
     long long base = a.cursor ? *a.cursor : a.first;
     base += (long long)a.rank * a.B;
-    long long avail = a.n_total - base;
-    int nb = avail <= 0 ? 0 : (avail < a.B ? (int)avail : a.B);
+    const long long avail = a.n_total - base;
+    const int nb = avail <= 0 ? 0 : (avail < a.B ? (int)avail : a.B);
     const InT *img_base = reinterpret_cast<const InT *>(a.images) + base * PCNN_IMG;
     const uint8_t *lab_base = a.labels ? a.labels + base : nullptr;
 
-    if (t == 0) {
-        mbar_init(&S.mbar[0], 1);
-        mbar_init(&S.mbar[1], 1);
-        mbar_init(&S.mbar[2], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
+    init_barriers(S);
     const int b0 = blockIdx.x;
-    if (t == 0) {
-        mbar_expect_tx(&S.mbar[2], NPACK * 4);
-        bulk_g2s(S.params, a.params, NPACK * 4, &S.mbar[2]);
-        if (b0 < nb) {
-            mbar_expect_tx(&S.mbar[0], IMG_BYTES);
-            bulk_g2s(IS_U8 ? (void *)S.stage[0] : (void *)S.imgf[0], img_base + (long long)b0 * PCNN_IMG, IMG_BYTES, &S.mbar[0]);
-        }
+    if (id.t == 0) {
+        issue_params(S, a.params);
+        if (b0 < nb) issue_image(S, 0, img_base + (long long)b0 * PCNN_IMG);
     }
-    mbar_wait(&S.mbar[2], 0);
-
-    // persistent per-thread accumulators (TRAIN)
-    float dw_c1[25], dw_s1[16], dw_f[PCNN_F];
-    float bsum_c1 = 0.0f, bsum_s1 = 0.0f, gfb = 0.0f, err_acc = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 25; ++i) dw_c1[i] = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) dw_s1[i] = 0.0f;
-#pragma unroll
-    for (int i = 0; i < PCNN_F; ++i) dw_f[i] = 0.0f;
-    int wrong_local = 0;
-
+    Acc A;
+    A.zero();
     int li = 0;
     for (int b = b0; b < nb; b += gridDim.x, ++li) {
-        const int buf = li & 1;
-        const unsigned parity = (li >> 1) & 1;
-        // ---- P0: image b has landed; convert to fp32 (u8 path), fetch the label
-        mbar_wait(&S.mbar[buf], parity);
-        if (IS_U8) {
-            if (t < 196) {
-                uchar4 q = reinterpret_cast<const uchar4 *>(S.stage[buf])[t];
-                float4 f = make_float4(pixel_to_float(q.x), pixel_to_float(q.y), pixel_to_float(q.z), pixel_to_float(q.w));
-                reinterpret_cast<float4 *>(S.imgf[buf])[t] = f;
-            }
-        }
-        if (t == NWK && lab_base) S.label[buf] = (int)lab_base[b];
-        __syncthreads();                                                         // sync #1
-        if (t == 0) {                                                            // prefetch the next image of this CTA
-            int bn = b + gridDim.x;
-            if (bn < nb) {
-                mbar_expect_tx(&S.mbar[buf ^ 1], IMG_BYTES);
-                bulk_g2s(IS_U8 ? (void *)S.stage[buf ^ 1] : (void *)S.imgf[buf ^ 1], img_base + (long long)bn * PCNN_IMG,
-                         IMG_BYTES, &S.mbar[buf ^ 1]);
-            }
-        }
-
-        // ---- P1: c1 (5x5 valid conv, layer.h:105-140) + sigmoid, s1 (4x4/4 weighted sum, layer.h:143-181) + sigmoid
-        float o[16];         // this worker's 4x4 block of c1 outputs
-        float s1o = 0.0f;    // its s1 output
-        float fcp[PCNN_F];
-#pragma unroll
-        for (int q = 0; q < PCNN_F; ++q) fcp[q] = 0.0f;
-        if (worker) {
-            const float *ip = S.imgf[buf] + (4 * wx) * 28 + 4 * wy;
-            float in[8][8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
-                float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
-                in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = lo.z; in[r][3] = lo.w;
-                in[r][4] = hi.x; in[r][5] = hi.y; in[r][6] = hi.z; in[r][7] = hi.w;
-            }
-            float acc[16];
-#pragma unroll
-            for (int p = 0; p < 16; ++p) acc[p] = 0.0f;
-            const float *wc = S.params + OFF_C1W + m * 25;
-#pragma unroll
-            for (int i = 0; i < 5; ++i)
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    const float w = wc[i * 5 + j];
-#pragma unroll
-                    for (int ox = 0; ox < 4; ++ox)
-#pragma unroll
-                        for (int oy = 0; oy < 4; ++oy) acc[ox * 4 + oy] = fmaf(in[ox + i][oy + j], w, acc[ox * 4 + oy]);
-                }
-            const float bc = S.params[OFF_C1B + m];
-            float s1pre = 0.0f;
-#pragma unroll
-            for (int p = 0; p < 16; ++p) {
-                o[p] = sigmoid_fast(acc[p] + bc);
-                s1pre = fmaf(S.params[OFF_S1W + p], o[p], s1pre);
-            }
-            s1o = sigmoid_fast(s1pre + S.params[OFF_S1B]);
-            // fp_preact_f partial products (layer.h:184-203): this worker owns input k = t
-#pragma unroll
-            for (int q = 0; q < PCNN_F; ++q) fcp[q] = S.params[OFF_FW + q * PCNN_S1 + t] * s1o;
-        } else {
-#pragma unroll
-            for (int p = 0; p < 16; ++p) o[p] = 0.0f;
-        }
-#pragma unroll
-        for (int q = 0; q < PCNN_F; ++q) {
-            float v = warp_sum(fcp[q]);
-            if (lane == 0) S.fc_red[warp][q] = v;
-        }
-        __syncthreads();                                                         // sync #2
-
-        // ---- P2: f layer output, makeError (layer.h:91-95), vectorNorm (Main.cpp:28-34)
-        if (warp == 0) {
-            float d = 0.0f, outv = 0.0f;
-            if (lane < PCNN_F) {
-                float pre = 0.0f;
-#pragma unroll
-                for (int w = 0; w < NWARP; ++w) pre += S.fc_red[w][lane];
-                pre += S.params[OFF_FB + lane];                                  // fp_bias_f, layer.h:206-211
-                outv = sigmoid_fast(pre);
-                if (TRAIN) {
-                    const int y = S.label[buf];
-                    d = (lane == y ? 1.0f : 0.0f) - outv;
-                    S.dpre_f[lane] = d;
-                    gfb += d;
-                } else {
-                    S.f_out[lane] = outv;
-                    if (a.f_out) a.f_out[(long long)b * PCNN_F + lane] = outv;
-                }
-            }
-            if (TRAIN) {
-                float ss = warp_sum(d * d);
-                if (lane == 0) err_acc += sqrtf(ss);
-            } else {
-                __syncwarp();
-                if (lane == 0) {                                                 // classify(), Main.cpp:193-197
-                    int best = 0;
-#pragma unroll
-                    for (int q = 1; q < PCNN_F; ++q)
-                        if (S.f_out[best] < S.f_out[q]) best = q;
-                    if (a.pred) a.pred[b] = (uint8_t)best;
-                    if (lab_base && best != S.label[buf]) ++wrong_local;
-                }
-            }
-        }
-        if (!TRAIN) continue;   // next iteration's sync #1 orders the reuse of fc_red / f_out
-        __syncthreads();                                                         // sync #3
-
-        // ---- P3: backward chain (Main.cpp:114-131)
-        if (worker) {
-            float dout_s1 = 0.0f;
-#pragma unroll
-            for (int q = 0; q < PCNN_F; ++q) {
-                const float dq = S.dpre_f[q];
-                dw_f[q] = fmaf(dq, s1o, dw_f[q]);                                          // bp_weight_f, layer.h:214-227
-                dout_s1 = fmaf(S.params[OFF_FW + q * PCNN_S1 + t], dq, dout_s1);            // bp_output_s1, layer.h:237-257
-            }
-            const float dpre_s1 = dout_s1 * s1o * (1.0f - s1o);                            // bp_preact_s1, layer.h:260-270
-            bsum_s1 += dpre_s1;                                                             // bp_bias_s1 accumulator, layer.h:303-314
-            float dpc[16];
-            float bs = 0.0f;
-#pragma unroll
-            for (int p = 0; p < 16; ++p) {
-                dw_s1[p] = fmaf(dpre_s1, o[p], dw_s1[p]);                                   // bp_weight_s1, layer.h:272-300
-                const float dout_c1 = S.params[OFF_S1W + p] * dpre_s1;                      // bp_output_c1, layer.h:319-346
-                dpc[p] = dout_c1 * (o[p] * (1.0f - o[p]));                                  // bp_preact_c1, layer.h:348-369
-                bs += dpc[p];
-            }
-            bsum_c1 += bs;                                                                  // bp_bias_c1 accumulator, layer.h:400-410
-            // bp_weight_c1, layer.h:371-395 (the /576 is applied once in the epilogue)
-            const float *ip = S.imgf[buf] + (4 * wx) * 28 + 4 * wy;
-            float in[8][8];
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
-                float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
-                in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = lo.z; in[r][3] = lo.w;
-                in[r][4] = hi.x; in[r][5] = hi.y; in[r][6] = hi.z; in[r][7] = hi.w;
-            }
-#pragma unroll
-            for (int i = 0; i < 5; ++i)
-#pragma unroll
-                for (int j = 0; j < 5; ++j) {
-                    float s = dw_c1[i * 5 + j];
-#pragma unroll
-                    for (int ox = 0; ox < 4; ++ox)
-#pragma unroll
-                        for (int oy = 0; oy < 4; ++oy) s = fmaf(dpc[ox * 4 + oy], in[ox + i][oy + j], s);
-                    dw_c1[i * 5 + j] = s;
-                }
-        }
+        const int bn = b + gridDim.x;
+        EvalOut ev;
+        ev.f_out = (!TRAIN && a.f_out) ? a.f_out + (long long)b * PCNN_F : nullptr;
+        ev.pred = (!TRAIN && a.pred) ? a.pred + b : nullptr;
+        ev.has_label = lab_base != nullptr;
+        image_pass<InT, TRAIN>(S, id, li, lab_base ? lab_base + b : nullptr,
+                               bn < nb ? img_base + (long long)bn * PCNN_IMG : nullptr, li == 0 ? 0 : -1, A, ev);
     }
-
     if (!TRAIN) {
-        if (t == 0 && a.wrong && wrong_local) atomicAdd(a.wrong, wrong_local);
+        if (id.t == 0 && a.wrong && A.wrong) atomicAdd(a.wrong, A.wrong);
+        if (li == 0) mbar_wait(&S.mbar[2], 0);   // never exit with the parameter copy still in flight
         return;
     }
-
-    // ---- epilogue: reduce the register accumulators over the CTA in a fixed order and publish the slot
-    float *slot = a.slots + (long long)blockIdx.x * NPACK;
-    __syncthreads();
-    if (worker) {
-#pragma unroll
-        for (int i = 0; i < 25; ++i) S.red[t * RED_STRIDE + i] = dw_c1[i];
-        S.red[t * RED_STRIDE + 25] = bsum_c1;
-#pragma unroll
-        for (int q = 0; q < PCNN_F; ++q) slot[OFF_FW + q * PCNN_S1 + t] = dw_f[q];      // column t is private to this worker
-    }
-#pragma unroll
-    for (int p = 0; p < 16; ++p) {
-        float v = warp_sum(dw_s1[p]);
-        if (lane == 0) S.red_s1[warp][p] = v;
-    }
-    {
-        float v = warp_sum(bsum_s1);
-        if (lane == 0) S.red_s1[warp][16] = v;
-    }
-    __syncthreads();
-    if (t < 150) {                       // c1 taps: sum over the 36 windows of map t / 25
-        const int mm = t / 25, ij = t % 25;
-        float s = 0.0f;
-#pragma unroll 4
-        for (int w = 0; w < 36; ++w) s += S.red[(mm * 36 + w) * RED_STRIDE + ij];
-        slot[OFF_C1W + t] = s * (1.0f / 576.0f);
-    } else if (t < 156) {                // c1 bias sums
-        const int mm = t - 150;
-        float s = 0.0f;
-#pragma unroll 4
-        for (int w = 0; w < 36; ++w) s += S.red[(mm * 36 + w) * RED_STRIDE + 25];
-        slot[OFF_C1B + mm] = s;
-    } else if (t < 173) {                // s1 taps and s1 bias sum
-        const int p = t - 156;
-        float s = 0.0f;
-#pragma unroll
-        for (int w = 0; w < NWARP; ++w) s += S.red_s1[w][p];
-        slot[OFF_S1W + p] = s;           // p == 16 lands on OFF_S1B
-    }
-    if (t < PCNN_F) slot[OFF_FB + t] = gfb;
-    if (t == 0) slot[OFF_ERR] = err_acc;
+    if (li == 0) mbar_wait(&S.mbar[2], 0);
+    cta_epilogue(S, id, A, a.slots + (long long)blockIdx.x * NPACK);
 }
-
 // ---- second kernel: fixed-order reduction of the per-CTA slots, optional update ------------------------------
 // block = 256 threads = 32 packed entries x 8 slot-phases; entry p of the packed vector is summed over slots
 // phase, phase+8, ... by each phase and the 8 partials are added in phase order.
@@ -373,30 +98,6 @@ struct ReduceArgs {
     int update;                 // 1: apply update here (single GPU); 0: leave grads for the all-reduce
 };
 
-__device__ __forceinline__ void apply_entry(float *params, int p, float g, float step) {
-    // reference operand order: w += step * g  (layer.h:99) ; bias += step * sum / n  (layer.h:316, :412)
-    if (p >= OFF_C1B && p < OFF_S1W) params[p] += step * g / 576.0f;
-    else if (p == OFF_S1B) params[p] += step * g / 216.0f;
-    else params[p] += step * g;
-}
-
-// rank_local == 0: all ranks index one shared split (rank r starts at cursor + r * B), the global batch is clamped at
-// the end of the split.  rank_local == 1: every rank walks its OWN equally sized shard (pcnn_learn_host), so the
-// per-rank batch is clamped and multiplied by world.
-__device__ __forceinline__ long long effective_global_batch(const long long *cursor, long long n_total, int B, int world,
-                                                            int rank_local) {
-    long long gb = (long long)B * world;
-    if (cursor) {
-        long long left = n_total - *cursor;
-        if (rank_local) {
-            if (left < B) gb = left * world;
-        } else if (left < gb) {
-            gb = left;
-        }
-    }
-    return gb < 1 ? 1 : gb;
-}
-
 __global__ void __launch_bounds__(256) k_reduce_slots(const ReduceArgs a) {
     __shared__ float part[8][33];
     const int pl = threadIdx.x & 31, phase = threadIdx.x >> 5;
@@ -413,8 +114,9 @@ __global__ void __launch_bounds__(256) k_reduce_slots(const ReduceArgs a) {
         a.grads[p] = g;
         if (a.update) {
             if (p < NPARAM) {
-                const float step = a.dt / (float)effective_global_batch(a.cursor_in, a.n_total, a.B, a.world, a.rank_local);
-                apply_entry(a.params, p, g, step);
+                const float step = a.dt / (float)effective_global_batch(a.cursor_in ? *a.cursor_in : 0, a.cursor_in != nullptr,
+                                                                        a.n_total, a.B, a.world, a.rank_local);
+                a.params[p] = updated_entry(a.params[p], p, g, step);
             } else {
                 *a.err_total += (double)g;
                 if (a.step_err) a.step_err[*a.step_idx & (STEP_ERR_CAP - 1)] = g;
@@ -448,8 +150,9 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     if (p >= NPACK) return;
     const float g = a.grads[p];
     if (p < NPARAM) {
-        const float step = a.dt / (float)effective_global_batch(a.cursor_in, a.n_total, a.B, a.world, a.rank_local);
-        apply_entry(a.params, p, g, step);
+        const float step = a.dt / (float)effective_global_batch(a.cursor_in ? *a.cursor_in : 0, a.cursor_in != nullptr, a.n_total,
+                                                                a.B, a.world, a.rank_local);
+        a.params[p] = updated_entry(a.params[p], p, g, step);
     } else {
         *a.err_total += (double)g;
         if (a.step_err) a.step_err[*a.step_idx & (STEP_ERR_CAP - 1)] = g;
@@ -656,7 +359,18 @@ static int get_step_graph(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, int
     return PCNN_OK;
 }
 
+static bool use_persistent(pcnn_ctx *ctx) {
+    const bool can = ctx->persist_cap > 0 && (ctx->world == 1 || ctx->p2p_ready);
+    if (ctx->step_mode == PCNN_MODE_GRAPH) return false;
+    return can;   // AUTO and PERSISTENT: whenever the persistent kernel can serve the configuration
+}
+
 static int run_cursor_steps(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nsteps, bool launch) {
+    if (ctx->step_mode == PCNN_MODE_PERSISTENT)
+        PCNN_REQUIRE(use_persistent(ctx), PCNN_ERR_STATE, "persistent mode requested but peers are not attached");
+    if (use_persistent(ctx)) return launch ? pcnn_persist_run(ctx, s, B, nsteps) : PCNN_OK;
+    PCNN_REQUIRE(ctx->world == 1 || ctx->nccl_comm, PCNN_ERR_STATE,
+                 "distributed steps need pcnn_comm_init_rank (graph mode) or pcnn_p2p_attach (persistent mode)");
     const bool distributed = ctx->world > 1 && ctx->nccl_comm;
     for (int size : GRAPH_SIZES) {
         while (nsteps >= size) {
@@ -914,9 +628,9 @@ namespace {
 __global__ void __launch_bounds__(256) k_fma_peak(float *out, float a, float b) {
     float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
 #pragma unroll 1
-    for (int i = 0; i < 4096; ++i) {
+    for (int i = 0; i < 256; ++i) {       // 256 FFMA per loop trip: loop overhead < 2 % of the issue slots
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 32; ++u) {
             x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
             x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
         }

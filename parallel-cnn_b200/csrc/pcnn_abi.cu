@@ -73,6 +73,10 @@ extern "C" int pcnn_create(pcnn_ctx **out, int device, void *stream) {
     PCNN_CUDA(cudaMemset(c->d_step_err, 0, STEP_ERR_CAP * sizeof(float)));
     PCNN_CUDA(cudaMalloc(&c->d_step_idx, sizeof(int)));
     PCNN_CUDA(cudaMemset(c->d_step_idx, 0, sizeof(int)));
+    PCNN_CUDA(cudaMalloc(&c->d_bar, sizeof(unsigned)));
+    PCNN_CUDA(cudaMemset(c->d_bar, 0, sizeof(unsigned)));
+    PCNN_CUDA(cudaMalloc(&c->d_abort, sizeof(int)));
+    PCNN_CUDA(cudaMemset(c->d_abort, 0, sizeof(int)));
     PCNN_CUDA(cudaMemset(c->d_params, 0, NPACK * sizeof(float)));
     PCNN_CUDA(cudaMemset(c->d_grads, 0, NPACK * sizeof(float)));
     PCNN_CUDA(cudaMemset(c->d_err_total, 0, sizeof(double)));
@@ -82,6 +86,7 @@ extern "C" int pcnn_create(pcnn_ctx **out, int device, void *stream) {
     {
         int rc = pcnn_fused_configure();
         if (rc) return rc;
+        if ((rc = pcnn_persist_configure(c))) return rc;
     }
     // default parameters = the reference's static-constructor state
     float init[NPARAM];
@@ -102,6 +107,10 @@ extern "C" int pcnn_destroy(pcnn_ctx *ctx) {
     pcnn_device_guard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     pcnn_comm_destroy(ctx);
+    pcnn_p2p_detach(ctx);
+    if (ctx->p2p_base) cudaFree(ctx->p2p_base);
+    if (ctx->d_bar) cudaFree(ctx->d_bar);
+    if (ctx->d_abort) cudaFree(ctx->d_abort);
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
     ctx->graphs.clear();
     release_split(ctx->split[0]);
@@ -134,7 +143,7 @@ extern "C" int pcnn_sync(pcnn_ctx *ctx) {
     PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_sync: ctx is NULL");
     pcnn_device_guard g(ctx->device);
     PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
-    return PCNN_OK;
+    return pcnn_persist_check(ctx);
 }
 
 extern "C" int pcnn_device_info(pcnn_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *hbm_bytes) {
@@ -279,6 +288,8 @@ extern "C" int pcnn_err_sum(pcnn_ctx *ctx, double *sum_out, int reset) {
     if (sum_out) {
         PCNN_CUDA(cudaMemcpyAsync(sum_out, ctx->d_err_total, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        int rc = pcnn_persist_check(ctx);
+        if (rc) return rc;
     }
     if (reset) PCNN_CUDA(cudaMemsetAsync(ctx->d_err_total, 0, sizeof(double), ctx->stream));
     return PCNN_OK;

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 #include <map>
 #include <tuple>
@@ -93,6 +94,21 @@ struct pcnn_ctx {
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
 
+    // persistent-kernel state (persist_kernels.cu)
+    int step_mode = PCNN_MODE_AUTO;
+    int persist_cap = 0;                    // co-resident CTAs of k_train_persist on this device
+    bool persist_used = false;
+    unsigned *d_bar = nullptr;              // grid barrier counter
+    int *d_abort = nullptr;                 // set by a spin loop that ran out of budget
+    unsigned p2p_step_id = 0;               // steps issued so far (flag values of the peer exchange)
+    void *p2p_base = nullptr;               // this rank's inbox + flags (IPC-exported)
+    bool p2p_ready = false;
+    float *p2p_inbox = nullptr;
+    unsigned *p2p_inflag = nullptr;
+    float *p2p_peer_inbox[PCNN_MAX_PEERS] = {};
+    unsigned *p2p_peer_inflag[PCNN_MAX_PEERS] = {};
+    void *p2p_mapped[PCNN_MAX_PEERS] = {};
+
     long launches = 0;
 };
 
@@ -128,5 +144,9 @@ int pcnn_fused_configure();
 int pcnn_launch_fused_grad(pcnn_ctx *ctx, const pcnn_step_src &src, int B, int *grid_out);
 int pcnn_launch_reduce(pcnn_ctx *ctx, int grid_slots, int B, const pcnn_step_src &src, bool update, bool record_err);
 int pcnn_launch_update(pcnn_ctx *ctx, int B, const pcnn_step_src &src, bool record_err);
+// persist_kernels.cu
+int pcnn_persist_configure(pcnn_ctx *ctx);
+int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nsteps);
+int pcnn_persist_check(pcnn_ctx *ctx);
 // comm.cu
 int pcnn_comm_allreduce_packed(pcnn_ctx *ctx);

@@ -1,0 +1,384 @@
+// parallel-cnn_b200/csrc/persist_kernels.cu -- the whole training loop as ONE persistent cooperative kernel.
+//
+// k_train_persist runs `nsteps` consecutive mini-batch steps without returning to the host.  Per step every CTA
+//   1. runs forward + backward for its images of the batch (fused_body.cuh, parameters in shared memory),
+//   2. publishes its packed partial gradient (slot), grid barrier,
+//   3. reduces ITS chunk of the packed vector over all slots in a fixed order (deterministic, no atomics),
+//      [N > 1: pushes the chunk into every peer GPU's inbox over NVLink (plain stores to IPC-mapped peer memory +
+//       a release flag), waits for the same chunk from every rank and adds them in rank order -- a fused
+//       reduce-scatter/all-gather with 2,344 floats per GPU per step and no second kernel],
+//      applies the SGD update to its chunk of the global parameters, grid barrier,
+//   4. reloads the 9.4 KB parameter block with a TMA bulk copy (overlapped with the next image's conversion).
+// The next step's first image is prefetched before the barriers, the sample cursor lives in registers, and launch
+// overhead, cursor kernels and per-step parameter prologues of the graph path disappear.  Cooperative launch
+// guarantees co-residency of the grid (2 CTAs/SM); every spin loop has a cycle budget and raises an abort flag
+// instead of hanging the GPU.
+//
+// Determinism: slot order, chunk order and rank order are fixed, so replicas stay bit-identical and reruns reproduce.
+#include "fused_body.cuh"
+
+using namespace pcnn_fused;
+
+namespace {
+
+constexpr long long SPIN_BUDGET = 6000000000LL;   // ~3 s at 2 GHz
+
+struct PersistArgs {
+    const void *images;
+    const uint8_t *labels;
+    long long n_total;
+    float *params;            // global packed parameters, updated in place every step
+    float *grads;             // packed gradient (+ error sum) of the most recent step
+    float *slots;             // [grid][NPACK]
+    unsigned *bar;            // grid barrier counter, zeroed by the host before the launch
+    long long *cursor;        // in/out: global sample position
+    double *err_total;
+    float *step_err;          // ring [STEP_ERR_CAP]
+    int *step_idx;            // in/out: ring position
+    int *abort_flag;
+    int B, nsteps, rank, world, rank_local;
+    float dt;
+    // peer exchange (world > 1)
+    float *inbox;             // local  [2][world][NPACK]
+    unsigned *inflag;         // local  [2][world][MAX_SLOTS]
+    float *peer_inbox[PCNN_MAX_PEERS];
+    unsigned *peer_inflag[PCNN_MAX_PEERS];
+    unsigned step_base;       // id of the step before the first one of this launch (ids are unique per context lifetime)
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// all CTAs of the (co-resident) grid; `target` = arrivals expected so far
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target, int *abort_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        red_release_gpu_add(bar, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire_gpu(bar) < target) {
+            if (*(volatile int *)abort_flag) break;
+            if (clock64() - t0 > SPIN_BUDGET) { *(volatile int *)abort_flag = 1; break; }
+        }
+    }
+    __syncthreads();
+}
+
+template <typename InT>
+__global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const PersistArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem<InT> &S = *reinterpret_cast<FusedSmem<InT> *>(smem_raw);
+    const ThreadId id;
+    const int t = id.t;
+    const int G = gridDim.x, c = blockIdx.x;
+    const InT *images = reinterpret_cast<const InT *>(a.images);
+
+    // reduce-phase geometry: this CTA owns packed entries [e0, e0 + cnt)
+    const int chunk = (NPACK + G - 1) / G;
+    const int e0 = c * chunk;
+    const int cnt = e0 >= NPACK ? 0 : (e0 + chunk > NPACK ? NPACK - e0 : chunk);
+    const int PH = chunk >= NT ? 1 : NT / chunk;         // slot phases when the chunk is narrower than the CTA
+
+    long long cursor = *a.cursor;
+    const int step_idx0 = *a.step_idx;
+    const long long stride = a.rank_local ? (long long)a.B : (long long)a.B * a.world;
+    auto shard = [&](long long cur, long long &base, int &nb) {
+        base = cur + (a.rank_local ? 0 : (long long)a.rank * a.B);
+        const long long avail = a.n_total - base;
+        nb = avail <= 0 ? 0 : (avail < a.B ? (int)avail : a.B);
+    };
+    long long base;
+    int nb;
+    shard(cursor, base, nb);
+
+    init_barriers(S);
+    int li = 0;                 // CTA-local running image counter (staging buffer + mbarrier phase)
+    unsigned pphase = 0;        // uses of the parameter barrier
+    unsigned nbar = 0;          // grid barriers passed
+    if (t == 0) {
+        issue_params(S, a.params);
+        if (c < nb) issue_image(S, 0, images + (base + c) * PCNN_IMG);
+    }
+
+    for (int s = 0; s < a.nsteps; ++s) {
+        // ---- 1. forward + backward over this CTA's images
+        Acc A;
+        A.zero();
+        const InT *img_base = images + base * PCNN_IMG;
+        const uint8_t *lab_base = a.labels + base;
+        bool first = true;
+        const EvalOut ev = {nullptr, nullptr, true};
+        for (int b = c; b < nb; b += G, ++li) {
+            const int bn = b + G;
+            image_pass<InT, true>(S, id, li, lab_base + b, bn < nb ? img_base + (long long)bn * PCNN_IMG : nullptr,
+                                  first ? (int)(pphase & 1) : -1, A, ev);
+            first = false;
+        }
+        if (first) mbar_wait(&S.mbar[2], pphase & 1);   // image-less CTAs still consume this parameter phase
+        ++pphase;
+        cta_epilogue(S, id, A, a.slots + (long long)c * NPACK);
+
+        // position of the next step; its first image is prefetched across the barriers
+        long long ncur = cursor + stride;
+        if (ncur >= a.n_total) ncur = 0;
+        long long nbase;
+        int nnb;
+        shard(ncur, nbase, nnb);
+        const bool more = s + 1 < a.nsteps;
+        if (t == 0 && more && c < nnb) issue_image(S, li & 1, images + (nbase + c) * PCNN_IMG);
+
+        nbar += 1;
+        grid_barrier(a.bar, nbar * (unsigned)G, a.abort_flag);                 // all slots published
+
+        // ---- 2. fixed-order reduction of my chunk over all slots (entry e of the chunk is owned by thread e % NT)
+        float *part = S.red;                                                   // [PH][chunk] when chunk < NT
+        const float step = a.dt / (float)effective_global_batch(cursor, true, a.n_total, a.B, a.world, a.rank_local);
+        const unsigned stepid = a.step_base + (unsigned)s + 1u;
+        const int par = (int)(stepid & 1u);
+        auto finalize = [&](int p, float g) {
+            a.grads[p] = g;
+            if (p < NPARAM) {
+                a.params[p] = updated_entry(__ldcg(a.params + p), p, g, step);
+            } else {
+                *a.err_total += (double)g;
+                a.step_err[(step_idx0 + s) & (STEP_ERR_CAP - 1)] = g;
+            }
+        };
+        auto publish = [&](int p, float g) {                                   // local result of one owned entry
+            if (a.world > 1) {
+                for (int q = 0; q < a.world; ++q) a.peer_inbox[q][((long long)par * a.world + a.rank) * NPACK + p] = g;
+            } else {
+                finalize(p, g);
+            }
+        };
+        if (chunk < NT) {
+            const int e = t % chunk, ph = t / chunk;
+            float sum = 0.0f;
+            if (e < cnt && ph < PH)
+                for (int k = ph; k < G; k += PH) sum += __ldcg(a.slots + (long long)k * NPACK + e0 + e);
+            if (ph < PH) part[ph * chunk + e] = sum;
+            __syncthreads();
+            if (t < cnt) {
+                float g = part[t];
+                for (int q = 1; q < PH; ++q) g += part[q * chunk + t];
+                publish(e0 + t, g);
+            }
+        } else {
+            for (int e = t; e < cnt; e += NT) {
+                float g = 0.0f;
+                for (int k = 0; k < G; ++k) g += __ldcg(a.slots + (long long)k * NPACK + e0 + e);
+                publish(e0 + e, g);
+            }
+        }
+        if (a.world > 1 && cnt > 0) {
+            // ---- 2b. exchange over NVLink: my chunk is now in every rank's inbox; flag it, collect everybody's chunk
+            __threadfence_system();
+            __syncthreads();
+            if (t < a.world) {
+                st_release_sys(a.peer_inflag[t] + ((long long)par * a.world + a.rank) * MAX_SLOTS + c, stepid);
+                const unsigned *f = a.inflag + ((long long)par * a.world + t) * MAX_SLOTS + c;
+                const long long t0 = clock64();
+                while (ld_acquire_sys(f) != stepid) {
+                    if (*(volatile int *)a.abort_flag) break;
+                    if (clock64() - t0 > 4 * SPIN_BUDGET) { *(volatile int *)a.abort_flag = 2; break; }
+                }
+            }
+            __syncthreads();
+            for (int e = t; e < cnt; e += NT) {
+                float g = 0.0f;
+                for (int q = 0; q < a.world; ++q)                              // rank order: identical on all GPUs
+                    g += __ldcv(a.inbox + ((long long)par * a.world + q) * NPACK + e0 + e);
+                finalize(e0 + e, g);
+            }
+        }
+        asm volatile("fence.proxy.async.global;" ::: "memory");               // parameter stores -> later bulk-copy reads
+
+        nbar += 1;
+        grid_barrier(a.bar, nbar * (unsigned)G, a.abort_flag);                 // parameters updated everywhere
+        if (t == 0 && more) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            issue_params(S, a.params);
+        }
+        cursor = ncur;
+        base = nbase;
+        nb = nnb;
+    }
+    if (c == 0 && t == 0) {
+        *a.cursor = cursor;
+        *a.step_idx = step_idx0 + a.nsteps;
+    }
+}
+
+template <typename InT> int persist_cap(int *out) {
+    int per_sm = 0;
+    cudaError_t e = cudaFuncSetAttribute(k_train_persist<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sizeof(FusedSmem<InT>));
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_train_persist<InT>, NT, sizeof(FusedSmem<InT>));
+    if (e != cudaSuccess) return pcnn_fail_cuda(e, "persistent kernel occupancy", __FILE__, __LINE__);
+    *out = per_sm;
+    return PCNN_OK;
+}
+
+}  // namespace
+
+int pcnn_persist_configure(pcnn_ctx *ctx) {
+    int a = 0, b = 0, rc;
+    if ((rc = persist_cap<uint8_t>(&a))) return rc;
+    if ((rc = persist_cap<float>(&b))) return rc;
+    int per_sm = a < b ? a : b;
+    if (per_sm > FUSED_CTAS_PER_SM) per_sm = FUSED_CTAS_PER_SM;
+    ctx->persist_cap = per_sm * ctx->sm_count;
+    if (ctx->persist_cap > MAX_SLOTS) ctx->persist_cap = MAX_SLOTS;
+    return PCNN_OK;
+}
+
+// nsteps cursor-driven steps of batch B over split `s` in one cooperative launch
+int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nsteps) {
+    PCNN_REQUIRE(ctx->persist_cap > 0, PCNN_ERR_STATE, "persistent kernel cannot be co-resident on this device");
+    PCNN_REQUIRE(ctx->world == 1 || ctx->p2p_ready, PCNN_ERR_STATE, "persistent multi-GPU steps need pcnn_p2p_attach");
+    while (nsteps > 0) {
+        const int k = nsteps > 1000000 ? 1000000 : (int)nsteps;   // keeps the 32-bit barrier counter in range
+        PersistArgs a{};
+        a.images = s.images;
+        a.labels = s.labels;
+        a.n_total = s.n;
+        a.params = ctx->d_params;
+        a.grads = ctx->d_grads;
+        a.slots = ctx->d_slots;
+        a.bar = ctx->d_bar;
+        a.cursor = ctx->d_cursor;
+        a.err_total = ctx->d_err_total;
+        a.step_err = ctx->d_step_err;
+        a.step_idx = ctx->d_step_idx;
+        a.abort_flag = ctx->d_abort;
+        a.B = B;
+        a.nsteps = k;
+        a.rank = ctx->rank;
+        a.world = ctx->world;
+        a.rank_local = s.rank_local ? 1 : 0;
+        a.dt = ctx->lr;
+        a.inbox = ctx->p2p_inbox;
+        a.inflag = ctx->p2p_inflag;
+        for (int q = 0; q < PCNN_MAX_PEERS; ++q) {
+            a.peer_inbox[q] = ctx->p2p_peer_inbox[q];
+            a.peer_inflag[q] = ctx->p2p_peer_inflag[q];
+        }
+        a.step_base = ctx->p2p_step_id;
+        ctx->p2p_step_id += (unsigned)k;
+        int grid = B < ctx->persist_cap ? B : ctx->persist_cap;
+        PCNN_CUDA(cudaMemsetAsync(ctx->d_bar, 0, sizeof(unsigned), ctx->stream));
+        void *args[] = {&a};
+        cudaError_t e;
+        if (s.pixel_type == PCNN_U8)
+            e = cudaLaunchCooperativeKernel((void *)k_train_persist<uint8_t>, dim3(grid), dim3(NT), args, sizeof(FusedSmem<uint8_t>), ctx->stream);
+        else
+            e = cudaLaunchCooperativeKernel((void *)k_train_persist<float>, dim3(grid), dim3(NT), args, sizeof(FusedSmem<float>), ctx->stream);
+        if (e != cudaSuccess) return pcnn_fail_cuda(e, "cudaLaunchCooperativeKernel(k_train_persist)", __FILE__, __LINE__);
+        ctx->launches += 1;
+        ctx->persist_used = true;
+        nsteps -= k;
+    }
+    return PCNN_OK;
+}
+
+// blocking check of the persistent kernel's abort flag (call after a stream synchronisation)
+int pcnn_persist_check(pcnn_ctx *ctx) {
+    if (!ctx->persist_used) return PCNN_OK;
+    int flag = 0;
+    PCNN_CUDA(cudaMemcpy(&flag, ctx->d_abort, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(ctx->d_abort, 0, sizeof(int));
+        pcnn_set_error("persistent training kernel aborted: %s wait exceeded its cycle budget",
+                       flag == 2 ? "peer-GPU exchange" : "grid barrier");
+        return PCNN_ERR_STATE;
+    }
+    return PCNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ peer memory plumbing
+struct p2p_layout {
+    static size_t inbox_bytes() { return (size_t)2 * PCNN_MAX_PEERS * NPACK * sizeof(float); }
+    static size_t flag_bytes() { return (size_t)2 * PCNN_MAX_PEERS * MAX_SLOTS * sizeof(unsigned); }
+};
+
+extern "C" int pcnn_p2p_export(pcnn_ctx *ctx, void *handle_out, size_t *handle_bytes) {
+    PCNN_REQUIRE(ctx && handle_out && handle_bytes, PCNN_ERR_ARG, "pcnn_p2p_export: NULL argument");
+    pcnn_device_guard g(ctx->device);
+    if (!ctx->p2p_base) {
+        PCNN_CUDA(cudaMalloc(&ctx->p2p_base, p2p_layout::inbox_bytes() + p2p_layout::flag_bytes()));
+        PCNN_CUDA(cudaMemset(ctx->p2p_base, 0, p2p_layout::inbox_bytes() + p2p_layout::flag_bytes()));
+    }
+    cudaIpcMemHandle_t h;
+    PCNN_CUDA(cudaIpcGetMemHandle(&h, ctx->p2p_base));
+    memcpy(handle_out, &h, sizeof(h));
+    *handle_bytes = sizeof(h);
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_p2p_attach(pcnn_ctx *ctx, const void *handles, int rank, int world) {
+    PCNN_REQUIRE(ctx && handles, PCNN_ERR_ARG, "pcnn_p2p_attach: NULL argument");
+    PCNN_REQUIRE(world >= 1 && world <= PCNN_MAX_PEERS && rank >= 0 && rank < world, PCNN_ERR_ARG,
+                 "pcnn_p2p_attach: bad rank %d / world %d (at most %d peers)", rank, world, PCNN_MAX_PEERS);
+    PCNN_REQUIRE(ctx->p2p_base, PCNN_ERR_STATE, "pcnn_p2p_attach: call pcnn_p2p_export first");
+    PCNN_REQUIRE(!ctx->p2p_ready, PCNN_ERR_STATE, "pcnn_p2p_attach: already attached");
+    PCNN_REQUIRE(ctx->world == 1 || (ctx->world == world && ctx->rank == rank), PCNN_ERR_STATE,
+                 "pcnn_p2p_attach: rank/world disagree with pcnn_comm_init_rank");
+    pcnn_device_guard g(ctx->device);
+    const cudaIpcMemHandle_t *hs = reinterpret_cast<const cudaIpcMemHandle_t *>(handles);
+    for (int q = 0; q < world; ++q) {
+        void *base = ctx->p2p_base;
+        if (q != rank) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, hs + q, sizeof(h));
+            PCNN_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            ctx->p2p_mapped[q] = base;
+        }
+        ctx->p2p_peer_inbox[q] = reinterpret_cast<float *>(base);
+        ctx->p2p_peer_inflag[q] = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(base) + p2p_layout::inbox_bytes());
+    }
+    ctx->p2p_inbox = ctx->p2p_peer_inbox[rank];
+    ctx->p2p_inflag = ctx->p2p_peer_inflag[rank];
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->p2p_ready = true;
+    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+    ctx->graphs.clear();
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_p2p_detach(pcnn_ctx *ctx) {
+    PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_p2p_detach: ctx is NULL");
+    pcnn_device_guard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int q = 0; q < PCNN_MAX_PEERS; ++q) {
+        if (ctx->p2p_mapped[q]) cudaIpcCloseMemHandle(ctx->p2p_mapped[q]);
+        ctx->p2p_mapped[q] = nullptr;
+        ctx->p2p_peer_inbox[q] = nullptr;
+        ctx->p2p_peer_inflag[q] = nullptr;
+    }
+    if (ctx->p2p_ready && !ctx->nccl_comm) { ctx->rank = 0; ctx->world = 1; }
+    ctx->p2p_ready = false;
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_set_step_mode(pcnn_ctx *ctx, int mode) {
+    PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_set_step_mode: ctx is NULL");
+    PCNN_REQUIRE(mode >= PCNN_MODE_AUTO && mode <= PCNN_MODE_PERSISTENT, PCNN_ERR_ARG, "pcnn_set_step_mode: bad mode %d", mode);
+    ctx->step_mode = mode;
+    return PCNN_OK;
+}

@@ -300,6 +300,23 @@ class Engine:
     def allreduce_grads(self):
         self._call("pcnn_allreduce_grads")
 
+    def p2p_export(self):
+        buf = (C.c_char * 128)()
+        n = C.c_size_t()
+        self._call("pcnn_p2p_export", buf, C.byref(n))
+        return bytes(buf[: n.value])
+
+    def p2p_attach(self, handles, rank, world):
+        """handles: list of the `world` byte strings returned by every rank's p2p_export(), in rank order"""
+        blob = b"".join(handles)
+        self._call("pcnn_p2p_attach", C.c_char_p(blob), int(rank), int(world))
+
+    def p2p_detach(self):
+        self._call("pcnn_p2p_detach")
+
+    def set_step_mode(self, mode):
+        self._call("pcnn_set_step_mode", int(mode))
+
     # ------------------------------------------------------------------ extension ops
     def maxpool_fwd(self, inp, out, argmax, planes, H, W, k):
         self._call("pcnn_maxpool_fwd", _p(inp), _p(out), _p(argmax), int(planes), int(H), int(W), int(k))

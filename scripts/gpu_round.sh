@@ -8,6 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > $
 echo "nproc=$(nproc)" >> $OUT/gpu.txt; lscpu | grep "Model name" >> $OUT/gpu.txt
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q --maxfail=30 -x -p no:cacheprovider > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -25 $OUT/pytest_gpu.log
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+if [ -n "${SWEEP:-}" ]; then echo "== sweep"; timeout 600 python scripts/sweep.py $SWEEP 2>&1 | tee $OUT/sweep.jsonl; fi
 echo "== bench"; timeout 900 python bench.py --steps ${STEPS:-4000} --warmup ${WARMUP:-200} > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"; cat $OUT/bench.json; tail -5 $OUT/bench.err
 if [ "${NCU:-1}" = "1" ]; then
   echo "== ncu launch list"
