@@ -7,7 +7,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "libpcnn.so")
+LIB_PATH = os.environ.get("PCNN_LIB_PATH") or os.path.join(HERE, "libpcnn.so")
 HEADER = os.path.join(ROOT, "include", "pcnn.h")
 
 NPARAM = 2343

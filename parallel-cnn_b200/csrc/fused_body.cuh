@@ -52,9 +52,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // 1 / (1 + e^-v) = 1 / (1 + 2^(-v log2 e)): MUFU.EX2 + MUFU.RCP.  The exponent product is rounded to fp32, so the
 // relative error of e^-v grows like |v| * 6e-8 (|v| < 30 here); the sigmoid inherits at most (1 - sigma) of it.
 __device__ __forceinline__ float sigmoid_fast(float v) {
+#ifdef PCNN_BISECT_OLD_SIGMOID
+    return __fdividef(1.0f, 1.0f + expf(-v));
+#else
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
     return __fdividef(1.0f, 1.0f + e);
+#endif
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -154,6 +158,10 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
     if (params_parity >= 0) mbar_wait(&S.mbar[2], (unsigned)params_parity);
     __syncthreads();                                                         // sync #1
     if (t == 0 && next_src) issue_image(S, buf ^ 1, next_src);
+    // Single-lane blocks (TMA issue by lane 0 of warp 0, label fetch by lane 24 of warp 6) leave their warp diverged:
+    // ptxas places the reconvergence point far downstream, and the butterfly shuffles below were then executed by
+    // a partial warp (observed on B200: warp 0's FC partial sums lost lane 0).  Reconverge explicitly.
+    __syncwarp();
 
     // ---- P1: c1 (5x5 valid conv, layer.h:105-140) + sigmoid, s1 (4x4/4 weighted sum, layer.h:143-181) + sigmoid
     float o[16];         // this worker's 4x4 block of c1 outputs
@@ -200,6 +208,7 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
 #pragma unroll
         for (int p = 0; p < 16; ++p) o[p] = 0.0f;
     }
+    __syncwarp();                                                            // workers / helpers of warp 6 rejoin
 #pragma unroll
     for (int q = 0; q < PCNN_F; ++q) {
         float v = warp_sum(fcp[q]);
@@ -227,6 +236,7 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
             }
         }
         if (TRAIN) {
+            __syncwarp();
             float ss = warp_sum(d * d);
             if (lane == 0) A.err_acc += sqrtf(ss);
         } else {
@@ -302,6 +312,7 @@ __device__ __forceinline__ void cta_epilogue(FusedSmem<InT> &S, const ThreadId &
 #pragma unroll
         for (int q = 0; q < PCNN_F; ++q) slot[OFF_FW + q * PCNN_S1 + t] = A.dw_f[q];   // column t is private to this worker
     }
+    __syncwarp();
 #pragma unroll
     for (int p = 0; p < 16; ++p) {
         float v = warp_sum(A.dw_s1[p]);

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_fused(const FusedArgs
         issue_params(S, a.params);
         if (b0 < nb) issue_image(S, 0, img_base + (long long)b0 * PCNN_IMG);
     }
+    __syncwarp();   // lane 0 rejoins its warp (see image_pass)
     Acc A;
     A.zero();
     int li = 0;

@@ -75,6 +75,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target, int
             if (clock64() - t0 > SPIN_BUDGET) { *(volatile int *)abort_flag = 1; break; }
         }
     }
+    __syncwarp();      // lane 0 rejoins its warp before the block barrier
     __syncthreads();
 }
 
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         issue_params(S, a.params);
         if (c < nb) issue_image(S, 0, images + (base + c) * PCNN_IMG);
     }
+    __syncwarp();   // lane 0 rejoins its warp (see image_pass)
 
     for (int s = 0; s < a.nsteps; ++s) {
         // ---- 1. forward + backward over this CTA's images
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         shard(ncur, nbase, nnb);
         const bool more = s + 1 < a.nsteps;
         if (t == 0 && more && c < nnb) issue_image(S, li & 1, images + (nbase + c) * PCNN_IMG);
+        __syncwarp();
 
         nbar += 1;
         grid_barrier(a.bar, nbar * (unsigned)G, a.abort_flag);                 // all slots published
@@ -213,6 +216,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
             asm volatile("fence.proxy.async.global;" ::: "memory");
             issue_params(S, a.params);
         }
+        __syncwarp();
         cursor = ncur;
         base = nbase;
         nb = nnb;
