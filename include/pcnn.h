@@ -195,6 +195,10 @@ int pcnn_p2p_detach(pcnn_ctx *ctx);
  * graphs of per-step kernels (+ NCCL all-reduce when distributed); PCNN_MODE_AUTO (default) = persistent whenever it
  * can serve the configuration (single GPU, or peers attached), else graph. */
 int pcnn_set_step_mode(pcnn_ctx *ctx, int mode);
+/* Phase timestamps of the persistent kernel (ns; 6 per step: step start, images done, slot published, barrier 1, chunk
+ * reduced/exchanged/updated, barrier 2; first 256 steps of a launch, CTA 0).  host_out == NULL arms tracing for the
+ * following launches, host_out != NULL reads the stamps back. */
+int pcnn_persist_trace(pcnn_ctx *ctx, long long *host_out, int cap_steps);
 
 /* ------------------------------------------------------------------ north_star extension ops (parity unpinned by the reference)
  * max-pool k x k stride k over [C][H][W] planes with argmax cache (flat index i*k+j, first maximum wins) */

@@ -97,6 +97,7 @@ _SIG = {
     "pcnn_p2p_attach": [_vp, _vp, _i, _i],
     "pcnn_p2p_detach": [_vp],
     "pcnn_set_step_mode": [_vp, _i],
+    "pcnn_persist_trace": [_vp, _vp, _i],
     "pcnn_maxpool_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
     "pcnn_maxpool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
     "pcnn_softmax_ce": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp],

@@ -109,6 +109,7 @@ extern "C" int pcnn_destroy(pcnn_ctx *ctx) {
     pcnn_comm_destroy(ctx);
     pcnn_p2p_detach(ctx);
     if (ctx->p2p_base) cudaFree(ctx->p2p_base);
+    if (ctx->d_trace) cudaFree(ctx->d_trace);
     if (ctx->d_bar) cudaFree(ctx->d_bar);
     if (ctx->d_abort) cudaFree(ctx->d_abort);
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);

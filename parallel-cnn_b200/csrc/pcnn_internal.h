@@ -22,7 +22,8 @@ constexpr int OFF_C1W = PCNN_OFF_C1W, OFF_C1B = PCNN_OFF_C1B, OFF_S1W = PCNN_OFF
 constexpr int FUSED_THREADS = 224;          // 216 workers (one per (map, 4x4 window)) + 8 helpers
 constexpr int FUSED_WORKERS = 216;
 constexpr int FUSED_CTAS_PER_SM = 2;
-constexpr int STEP_ERR_CAP = 4096;         // most steps one replayed graph may hold
+constexpr int PCNN_TRACE_STEPS = 256;      // steps per launch the persistent kernel can timestamp
+constexpr int STEP_ERR_CAP = 4096;        // most steps one replayed graph may hold
 constexpr int MAX_SLOTS = 148 * 4;          // upper bound on the fused grid (per-CTA partial-gradient slots)
 
 struct pcnn_split_binding {
@@ -100,13 +101,12 @@ struct pcnn_ctx {
     bool persist_used = false;
     unsigned *d_bar = nullptr;              // grid barrier counter
     int *d_abort = nullptr;                 // set by a spin loop that ran out of budget
+    long long *d_trace = nullptr;           // optional phase timestamps of the persistent kernel (pcnn_persist_trace)
     unsigned p2p_step_id = 0;               // steps issued so far (flag values of the peer exchange)
     void *p2p_base = nullptr;               // this rank's inbox + flags (IPC-exported)
     bool p2p_ready = false;
-    float *p2p_inbox = nullptr;
-    unsigned *p2p_inflag = nullptr;
-    float *p2p_peer_inbox[PCNN_MAX_PEERS] = {};
-    unsigned *p2p_peer_inflag[PCNN_MAX_PEERS] = {};
+    uint2 *p2p_inbox = nullptr;             // [2][PCNN_MAX_PEERS][NPACK] words {value bits, step id}
+    uint2 *p2p_peer_inbox[PCNN_MAX_PEERS] = {};
     void *p2p_mapped[PCNN_MAX_PEERS] = {};
 
     long launches = 0;

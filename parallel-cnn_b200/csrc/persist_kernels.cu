@@ -39,12 +39,23 @@ struct PersistArgs {
     int B, nsteps, rank, world, rank_local;
     float dt;
     // peer exchange (world > 1)
-    float *inbox;             // local  [2][world][NPACK]
-    unsigned *inflag;         // local  [2][world][MAX_SLOTS]
-    float *peer_inbox[PCNN_MAX_PEERS];
-    unsigned *peer_inflag[PCNN_MAX_PEERS];
+    uint2 *inbox;             // local  [2][world][NPACK] words {value bits, step id}
+    uint2 *peer_inbox[PCNN_MAX_PEERS];
     unsigned step_base;       // id of the step before the first one of this launch (ids are unique per context lifetime)
+    long long *trace;         // optional [PCNN_TRACE_STEPS][6] globaltimer stamps written by CTA 0 (pcnn_persist_trace)
 };
+
+__device__ __forceinline__ long long globaltimer_ns() {
+    long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+// phase boundaries of one step as seen by CTA 0: 0 step start, 1 images done, 2 slot published, 3 barrier 1 passed,
+// 4 chunk reduced/exchanged/updated, 5 barrier 2 passed
+#define PCNN_TRACE(k)                                                                              \
+    do {                                                                                           \
+        if (a.trace && c == 0 && t == 0 && s < PCNN_TRACE_STEPS) a.trace[s * 6 + (k)] = globaltimer_ns(); \
+    } while (0)
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
     unsigned v;
@@ -58,6 +69,15 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
 }
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// {value, step id} words of the peer exchange: one 8-byte volatile access each way (bypasses L1, single-copy atomic)
+__device__ __forceinline__ void st_ll(uint2 *p, float value, unsigned id) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(value)), "r"(id) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -118,6 +138,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
 
     for (int s = 0; s < a.nsteps; ++s) {
         // ---- 1. forward + backward over this CTA's images
+        PCNN_TRACE(0);
         Acc A;
         A.zero();
         const InT *img_base = images + base * PCNN_IMG;
@@ -132,7 +153,9 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         }
         if (first) mbar_wait(&S.mbar[2], pphase & 1);   // image-less CTAs still consume this parameter phase
         ++pphase;
+        PCNN_TRACE(1);
         cta_epilogue(S, id, A, a.slots + (long long)c * NPACK);
+        PCNN_TRACE(2);
 
         // position of the next step; its first image is prefetched across the barriers
         long long ncur = cursor + stride;
@@ -146,6 +169,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
 
         nbar += 1;
         grid_barrier(a.bar, nbar * (unsigned)G, a.abort_flag);                 // all slots published
+        PCNN_TRACE(3);
 
         // ---- 2. fixed-order reduction of my chunk over all slots (entry e of the chunk is owned by thread e % NT)
         float *part = S.red;                                                   // [PH][chunk] when chunk < NT
@@ -161,9 +185,13 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
                 a.step_err[(step_idx0 + s) & (STEP_ERR_CAP - 1)] = g;
             }
         };
+        // Peer exchange, "low-latency" style: every 8-byte inbox word carries {value, step id}.  An 8-byte store is
+        // single-copy atomic, so the receiver needs no flag round trip and the sender no system-scope fence: it polls
+        // the word until the step id matches.  One NVLink one-way latency per step.
         auto publish = [&](int p, float g) {                                   // local result of one owned entry
             if (a.world > 1) {
-                for (int q = 0; q < a.world; ++q) a.peer_inbox[q][((long long)par * a.world + a.rank) * NPACK + p] = g;
+                for (int q = 0; q < a.world; ++q)
+                    st_ll(a.peer_inbox[q] + ((long long)par * a.world + a.rank) * NPACK + p, g, stepid);
             } else {
                 finalize(p, g);
             }
@@ -188,30 +216,30 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
             }
         }
         if (a.world > 1 && cnt > 0) {
-            // ---- 2b. exchange over NVLink: my chunk is now in every rank's inbox; flag it, collect everybody's chunk
-            __threadfence_system();
-            __syncthreads();
-            if (t < a.world) {
-                st_release_sys(a.peer_inflag[t] + ((long long)par * a.world + a.rank) * MAX_SLOTS + c, stepid);
-                const unsigned *f = a.inflag + ((long long)par * a.world + t) * MAX_SLOTS + c;
-                const long long t0 = clock64();
-                while (ld_acquire_sys(f) != stepid) {
-                    if (*(volatile int *)a.abort_flag) break;
-                    if (clock64() - t0 > 4 * SPIN_BUDGET) { *(volatile int *)a.abort_flag = 2; break; }
-                }
-            }
-            __syncthreads();
+            // ---- 2b. collect every rank's value of my entries (they arrive over NVLink) and add them in rank order
             for (int e = t; e < cnt; e += NT) {
                 float g = 0.0f;
-                for (int q = 0; q < a.world; ++q)                              // rank order: identical on all GPUs
-                    g += __ldcv(a.inbox + ((long long)par * a.world + q) * NPACK + e0 + e);
+                for (int q = 0; q < a.world; ++q) {                            // rank order: identical on all GPUs
+                    const uint2 *w = a.inbox + ((long long)par * a.world + q) * NPACK + e0 + e;
+                    uint2 v = ld_ll(w);
+                    const long long t0 = clock64();
+                    while (v.y != stepid) {
+                        if (*(volatile int *)a.abort_flag) break;
+                        if (clock64() - t0 > 4 * SPIN_BUDGET) { *(volatile int *)a.abort_flag = 2; break; }
+                        v = ld_ll(w);
+                    }
+                    g += __uint_as_float(v.x);
+                }
                 finalize(e0 + e, g);
             }
+            __syncwarp();
         }
         asm volatile("fence.proxy.async.global;" ::: "memory");               // parameter stores -> later bulk-copy reads
+        PCNN_TRACE(4);
 
         nbar += 1;
         grid_barrier(a.bar, nbar * (unsigned)G, a.abort_flag);                 // parameters updated everywhere
+        PCNN_TRACE(5);
         if (t == 0 && more) {
             asm volatile("fence.proxy.async.global;" ::: "memory");
             issue_params(S, a.params);
@@ -277,11 +305,10 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
         a.rank_local = s.rank_local ? 1 : 0;
         a.dt = ctx->lr;
         a.inbox = ctx->p2p_inbox;
-        a.inflag = ctx->p2p_inflag;
         for (int q = 0; q < PCNN_MAX_PEERS; ++q) {
             a.peer_inbox[q] = ctx->p2p_peer_inbox[q];
-            a.peer_inflag[q] = ctx->p2p_peer_inflag[q];
         }
+        a.trace = ctx->d_trace;
         a.step_base = ctx->p2p_step_id;
         ctx->p2p_step_id += (unsigned)k;
         int grid = B < ctx->persist_cap ? B : ctx->persist_cap;
@@ -316,16 +343,15 @@ int pcnn_persist_check(pcnn_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------ peer memory plumbing
 struct p2p_layout {
-    static size_t inbox_bytes() { return (size_t)2 * PCNN_MAX_PEERS * NPACK * sizeof(float); }
-    static size_t flag_bytes() { return (size_t)2 * PCNN_MAX_PEERS * MAX_SLOTS * sizeof(unsigned); }
+    static size_t inbox_bytes() { return (size_t)2 * PCNN_MAX_PEERS * NPACK * sizeof(uint2); }
 };
 
 extern "C" int pcnn_p2p_export(pcnn_ctx *ctx, void *handle_out, size_t *handle_bytes) {
     PCNN_REQUIRE(ctx && handle_out && handle_bytes, PCNN_ERR_ARG, "pcnn_p2p_export: NULL argument");
     pcnn_device_guard g(ctx->device);
     if (!ctx->p2p_base) {
-        PCNN_CUDA(cudaMalloc(&ctx->p2p_base, p2p_layout::inbox_bytes() + p2p_layout::flag_bytes()));
-        PCNN_CUDA(cudaMemset(ctx->p2p_base, 0, p2p_layout::inbox_bytes() + p2p_layout::flag_bytes()));
+        PCNN_CUDA(cudaMalloc(&ctx->p2p_base, p2p_layout::inbox_bytes()));
+        PCNN_CUDA(cudaMemset(ctx->p2p_base, 0, p2p_layout::inbox_bytes()));
     }
     cudaIpcMemHandle_t h;
     PCNN_CUDA(cudaIpcGetMemHandle(&h, ctx->p2p_base));
@@ -352,11 +378,9 @@ extern "C" int pcnn_p2p_attach(pcnn_ctx *ctx, const void *handles, int rank, int
             PCNN_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
             ctx->p2p_mapped[q] = base;
         }
-        ctx->p2p_peer_inbox[q] = reinterpret_cast<float *>(base);
-        ctx->p2p_peer_inflag[q] = reinterpret_cast<unsigned *>(reinterpret_cast<char *>(base) + p2p_layout::inbox_bytes());
+        ctx->p2p_peer_inbox[q] = reinterpret_cast<uint2 *>(base);
     }
     ctx->p2p_inbox = ctx->p2p_peer_inbox[rank];
-    ctx->p2p_inflag = ctx->p2p_peer_inflag[rank];
     ctx->rank = rank;
     ctx->world = world;
     ctx->p2p_ready = true;
@@ -373,10 +397,27 @@ extern "C" int pcnn_p2p_detach(pcnn_ctx *ctx) {
         if (ctx->p2p_mapped[q]) cudaIpcCloseMemHandle(ctx->p2p_mapped[q]);
         ctx->p2p_mapped[q] = nullptr;
         ctx->p2p_peer_inbox[q] = nullptr;
-        ctx->p2p_peer_inflag[q] = nullptr;
     }
     if (ctx->p2p_ready && !ctx->nccl_comm) { ctx->rank = 0; ctx->world = 1; }
     ctx->p2p_ready = false;
+    return PCNN_OK;
+}
+
+// Phase timestamps (ns, %globaltimer) of the first PCNN_TRACE_STEPS steps of the NEXT persistent launches as seen by
+// CTA 0: enable with host_out == NULL (allocates and clears the device buffer), read back with host_out != NULL.
+extern "C" int pcnn_persist_trace(pcnn_ctx *ctx, long long *host_out, int cap_steps) {
+    PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_persist_trace: ctx is NULL");
+    pcnn_device_guard g(ctx->device);
+    const size_t bytes = (size_t)PCNN_TRACE_STEPS * 6 * sizeof(long long);
+    if (!host_out) {
+        if (!ctx->d_trace) PCNN_CUDA(cudaMalloc((void **)&ctx->d_trace, bytes));
+        PCNN_CUDA(cudaMemsetAsync(ctx->d_trace, 0, bytes, ctx->stream));
+        return PCNN_OK;
+    }
+    PCNN_REQUIRE(ctx->d_trace, PCNN_ERR_STATE, "pcnn_persist_trace: tracing was not enabled");
+    PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int n = cap_steps < PCNN_TRACE_STEPS ? cap_steps : PCNN_TRACE_STEPS;
+    PCNN_CUDA(cudaMemcpy(host_out, ctx->d_trace, (size_t)n * 6 * sizeof(long long), cudaMemcpyDeviceToHost));
     return PCNN_OK;
 }
 

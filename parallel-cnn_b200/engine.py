@@ -317,6 +317,14 @@ class Engine:
     def set_step_mode(self, mode):
         self._call("pcnn_set_step_mode", int(mode))
 
+    def persist_trace_arm(self):
+        self._call("pcnn_persist_trace", None, 0)
+
+    def persist_trace_read(self, steps=256):
+        out = np.zeros((steps, 6), np.int64)
+        self._call("pcnn_persist_trace", out.ctypes.data, int(steps))
+        return out
+
     # ------------------------------------------------------------------ extension ops
     def maxpool_fwd(self, inp, out, argmax, planes, H, W, k):
         self._call("pcnn_maxpool_fwd", _p(inp), _p(out), _p(argmax), int(planes), int(H), int(W), int(k))
