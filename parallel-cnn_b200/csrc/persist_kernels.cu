@@ -86,8 +86,9 @@ __device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) {
 // all CTAs of the (co-resident) grid; `target` = arrivals expected so far
 __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target, int *abort_flag) {
     __syncthreads();
+    if (gridDim.x == 1) return;        // a single CTA: the block barrier is the grid barrier
     if (threadIdx.x == 0) {
-        __threadfence();
+        // release-add: cumulative over the CTA's writes ordered before it by the block barrier above
         red_release_gpu_add(bar, 1u);
         const long long t0 = clock64();
         while (ld_acquire_gpu(bar) < target) {
@@ -176,10 +177,10 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         const float step = a.dt / (float)effective_global_batch(cursor, true, a.n_total, a.B, a.world, a.rank_local);
         const unsigned stepid = a.step_base + (unsigned)s + 1u;
         const int par = (int)(stepid & 1u);
-        auto finalize = [&](int p, float g) {
+        auto finalize = [&](int p, float g, float w_old) {
             a.grads[p] = g;
             if (p < NPARAM) {
-                a.params[p] = updated_entry(__ldcg(a.params + p), p, g, step);
+                a.params[p] = updated_entry(w_old, p, g, step);
             } else {
                 *a.err_total += (double)g;
                 a.step_err[(step_idx0 + s) & (STEP_ERR_CAP - 1)] = g;
@@ -188,36 +189,65 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         // Peer exchange, "low-latency" style: every 8-byte inbox word carries {value, step id}.  An 8-byte store is
         // single-copy atomic, so the receiver needs no flag round trip and the sender no system-scope fence: it polls
         // the word until the step id matches.  One NVLink one-way latency per step.
-        auto publish = [&](int p, float g) {                                   // local result of one owned entry
+        auto publish = [&](int p, float g, float w_old) {                      // local result of one owned entry
             if (a.world > 1) {
                 for (int q = 0; q < a.world; ++q)
                     st_ll(a.peer_inbox[q] + ((long long)par * a.world + a.rank) * NPACK + p, g, stepid);
             } else {
-                finalize(p, g);
+                finalize(p, g, w_old);
             }
         };
+        constexpr int MAXE = (NPACK + NT - 1) / NT;                            // entries a thread can own (G == 1)
+        float w_mine[MAXE];                                                    // old parameter values, requested early
         if (chunk < NT) {
             const int e = t % chunk, ph = t / chunk;
+            w_mine[0] = (t < cnt && e0 + t < NPARAM) ? __ldcg(a.params + e0 + t) : 0.0f;
             float sum = 0.0f;
-            if (e < cnt && ph < PH)
-                for (int k = ph; k < G; k += PH) sum += __ldcg(a.slots + (long long)k * NPACK + e0 + e);
+            if (e < cnt && ph < PH) {
+                const float *sp = a.slots + e0 + e;
+                for (int k0 = ph; k0 < G; k0 += 8 * PH) {                      // 8 loads in flight, added in slot order
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int k = k0 + u * PH;
+                        v[u] = k < G ? __ldcg(sp + (long long)k * NPACK) : 0.0f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) sum += v[u];
+                }
+            }
             if (ph < PH) part[ph * chunk + e] = sum;
             __syncthreads();
             if (t < cnt) {
                 float g = part[t];
                 for (int q = 1; q < PH; ++q) g += part[q * chunk + t];
-                publish(e0 + t, g);
+                publish(e0 + t, g, w_mine[0]);
             }
-        } else {
-            for (int e = t; e < cnt; e += NT) {
-                float g = 0.0f;
-                for (int k = 0; k < G; ++k) g += __ldcg(a.slots + (long long)k * NPACK + e0 + e);
-                publish(e0 + e, g);
+        } else {                                                               // G <= 10: a thread owns up to MAXE entries
+            float gs[MAXE];
+#pragma unroll
+            for (int i = 0; i < MAXE; ++i) {
+                const int e = t + i * NT;
+                gs[i] = 0.0f;
+                w_mine[i] = 0.0f;
+                if (e < cnt) {
+                    const int p = e0 + e;
+                    if (p < NPARAM) w_mine[i] = __ldcg(a.params + p);
+                    float acc = 0.0f;
+                    for (int k = 0; k < G; ++k) acc += __ldcg(a.slots + (long long)k * NPACK + p);
+                    gs[i] = acc;
+                }
             }
+#pragma unroll
+            for (int i = 0; i < MAXE; ++i)
+                if (t + i * NT < cnt) publish(e0 + t + i * NT, gs[i], w_mine[i]);
         }
         if (a.world > 1 && cnt > 0) {
             // ---- 2b. collect every rank's value of my entries (they arrive over NVLink) and add them in rank order
-            for (int e = t; e < cnt; e += NT) {
+#pragma unroll
+            for (int i = 0; i < MAXE; ++i) {
+                const int e = t + i * NT;
+                if (e >= cnt) break;
                 float g = 0.0f;
                 for (int q = 0; q < a.world; ++q) {                            // rank order: identical on all GPUs
                     const uint2 *w = a.inbox + ((long long)par * a.world + q) * NPACK + e0 + e;
@@ -230,7 +260,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
                     }
                     g += __uint_as_float(v.x);
                 }
-                finalize(e0 + e, g);
+                finalize(e0 + e, g, w_mine[i]);
             }
             __syncwarp();
         }
