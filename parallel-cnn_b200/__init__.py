@@ -12,7 +12,7 @@ from ._lib import (  # noqa: F401
     LIB_PATH, NPARAM, OFF, PcnnError, U8, F32, TRAIN_SET, TEST_SET, MODE_AUTO, MODE_GRAPH, MODE_PERSISTENT,
     lib, declared_symbols, init_params_reference, mnist_load_u8,
 )
-from .engine import DeviceArray, Engine  # noqa: F401
+from .engine import ConvPlan, DeviceArray, Engine, bf16_bits_to_f32, f32_to_bf16_bits  # noqa: F401
 
 __all__ = ["Engine", "DeviceArray", "PcnnError", "lib", "declared_symbols", "init_params_reference",
            "mnist_load_u8", "NPARAM", "OFF", "U8", "F32", "TRAIN_SET", "TEST_SET", "LIB_PATH"]

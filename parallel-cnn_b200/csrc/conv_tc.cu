@@ -1,0 +1,401 @@
+// parallel-cnn_b200/csrc/conv_tc.cu -- bf16 convolution forward on the 5th-generation tensor cores (SURVEY.md x3,
+// BASELINE.json configs 3 and 5): tcgen05.mma with TMEM accumulators, operands staged by TMA, no im2col pass.
+//
+// Formulation ("row-Toeplitz implicit GEMM").  The reference's conv is a valid, stride-1 cross-correlation
+// (Sequential/layer.h:118-130); for NHWC activations one output row is
+//     y[n][p][q][k] = sum_r  sum_{(w,c)}  x[n][p+r][w][c] * T_r[(w,c)][(q,k)],      T_r[(w,c)][(q,k)] = f[k][r][w-q][c]
+// i.e. R GEMMs whose A operand is simply the input row p+r (W*C contiguous elements) and whose B operand is a banded
+// Toeplitz matrix that depends only on (w - q).  Tiling the output row into blocks of Qt pixels makes the band a
+// small CONSTANT matrix: for a block starting at q0 only the (Qt+S-1)*C <= 32 input elements from column q0*C matter,
+// and T_r restricted to them is the same [32 x Qt*K] matrix for every block, every row and every image.  So
+//   * A tiles are plain 2-D TMA boxes [128 rows x 32 elements] of the activation tensor viewed as [N*H][W*C]
+//     (row r of the filter = the same box shifted down by r rows): zero im2col traffic, the 16x..25x expansion of
+//     im2col never exists anywhere, not even in shared memory;
+//   * B = R matrices [Qt*K x 32] (<= 48 KB) built once on the host from the filter bank, resident in shared memory;
+//   * D = [128 x Qt*K] fp32 in TMEM (256 columns, double buffered = the whole 512-column TMEM of the SM);
+//   * per tile 2*R tcgen05.mma (M=128, N=Qt*K, K=16) issued by one elected thread, epilogue (bias, optional sigmoid,
+//     bf16 pack, store) by four warps reading TMEM with tcgen05.ld while the next tile's MMAs run.
+// Density: LeNet c1 (C=1, K=6, 5x5, Qt=24): 25/32 of K and 6*24/144 of N are useful but the band itself is sparse
+// (17 % of the issued MACs are useful); config 5 (C=3, K=64, 3x3, Qt=4): 28 %.  The tensor pipe has > 10x headroom over
+// the HBM time of these layers (AI 10-26 flop/B), which is the point: the layer is HBM-bound and the tensor cores are
+// what lets a bf16 kernel reach the HBM roofline where the fp32 FMA pipe cannot.
+//
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2-5 = epilogue (TMEM lane quarter = warp % 4).
+#include "pcnn_internal.h"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <vector>
+
+namespace {
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_M = 128;          // output rows per tile (TMEM lanes)
+constexpr int TC_KCHUNK = 32;      // bf16 elements per filter row r (64 B = one SWIZZLE_64B span)
+constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_R = 5;
+constexpr int A_TILE_BYTES = TC_M * TC_KCHUNK * 2;   // 8 KB
+
+struct ConvTcParams {
+    int n_img, H, P, Q, K, R;      // images, input rows per image, valid output rows/cols, filters, filter rows
+    int Qt, ncols;                 // output pixels per tile, Qt * K
+    int C;                         // input channels (column offset of a tile = q0 * C elements)
+    int n_mtiles, n_qtiles;
+    int act;                       // 0: none, 1: sigmoid (the reference's activation, layer.h:81-83)
+    long long y_row_elems;         // Q * K
+    __nv_bfloat16 *y;
+    const float *bias;             // [K] or null
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(unsigned long long *b, unsigned n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(n));
+}
+__device__ __forceinline__ void bar_expect_tx(unsigned long long *b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(unsigned long long *b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(unsigned long long *b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "TC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TC_DONE;\n"
+        "bra TC_WAIT;\n"
+        "TC_DONE:\n"
+        "}\n" ::"r"(s_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     s_u32(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(s_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives row (lane base + i)
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile with 64-byte rows written by TMA with CU_TENSOR_MAP_SWIZZLE_64B: canonical layout
+// Swizzle<2,4,3> o ((8,n),2):((4,SBO),1) in 16-byte units (cute/arch/mma_sm100_desc.hpp): 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4)        // start address, bits [0,14)
+           | (1ull << 16)                                  // leading byte offset (unused for swizzled K-major)
+           | ((uint64_t)(512 >> 4) << 32)                  // stride byte offset: 8 rows * 64 B
+           | (1ull << 46)                                  // descriptor version (Blackwell)
+           | (4ull << 61);                                 // layout type SWIZZLE_64B
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct alignas(1024) ConvTcSmem {
+    unsigned char a[TC_STAGES][TC_MAX_R][A_TILE_BYTES];   // 3 x 5 x 8 KB = 120 KB
+    unsigned char b[TC_MAX_R][256 * TC_KCHUNK * 2];       // 5 x 16 KB = 80 KB
+    float bias[256];
+    unsigned long long full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2], bfull;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const ConvTcParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    ConvTcSmem &S = *reinterpret_cast<ConvTcSmem *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = p.n_mtiles * p.n_qtiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_STAGES; ++i) { bar_init(&S.full[i], 1); bar_init(&S.empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { bar_init(&S.tfull[i], 1); bar_init(&S.tempty[i], 4); }
+        bar_init(&S.bfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 256; i += TC_THREADS) S.bias[i] = (p.bias && i < p.ncols) ? p.bias[i % p.K] : 0.0f;
+    if (warp == 1) {   // TMEM: all 512 columns (two accumulators of up to 256 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(&S.tmem_base)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = S.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer: the Toeplitz operand once, then R activation boxes per tile =====
+        if (lane == 0) {
+            bar_expect_tx(&S.bfull, (unsigned)(p.R * p.ncols * TC_KCHUNK * 2));
+            for (int r = 0; r < p.R; ++r) tma_load_2d(S.b[r], &map_b, 0, r * p.ncols, &S.bfull);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int stage = it % TC_STAGES;
+                const unsigned ph = (unsigned)(it / TC_STAGES) & 1u;
+                bar_wait(&S.empty[stage], ph ^ 1u);
+                const int mt = tile / p.n_qtiles, qt = tile % p.n_qtiles;
+                bar_expect_tx(&S.full[stage], (unsigned)(p.R * A_TILE_BYTES));
+                for (int r = 0; r < p.R; ++r)
+                    tma_load_2d(S.a[stage][r], &map_x, qt * p.Qt * p.C, mt * TC_M + r, &S.full[stage]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(TC_M, p.ncols);
+            bar_wait(&S.bfull, 0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int stage = it % TC_STAGES;
+                const unsigned ph = (unsigned)(it / TC_STAGES) & 1u;
+                const int acc = it & 1;
+                const unsigned aph = (unsigned)(it >> 1) & 1u;
+                bar_wait(&S.tempty[acc], aph ^ 1u);            // epilogue has drained this accumulator
+                bar_wait(&S.full[stage], ph);                   // activations have landed
+                tc_fence_after();
+                const uint32_t d = tmem + (uint32_t)(acc * 256);
+                for (int r = 0; r < p.R; ++r) {
+                    const uint32_t a0 = s_u32(S.a[stage][r]), b0 = s_u32(S.b[r]);
+#pragma unroll
+                    for (int ks = 0; ks < TC_KCHUNK / 16; ++ks)   // K = 16 bf16 = 32 bytes per instruction
+                        tc_mma_bf16(d, umma_desc_k_sw64(a0 + ks * 32), umma_desc_k_sw64(b0 + ks * 32), idesc,
+                                    (r | ks) != 0 ? 1u : 0u);
+                }
+                tc_commit(&S.empty[stage]);                     // smem stage reusable once these MMAs retire
+                tc_commit(&S.tfull[acc]);                       // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue warps: TMEM -> registers -> bias / activation -> bf16 -> global =====
+        const int quarter = warp & 3;                           // TMEM lanes this warp may read
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const unsigned aph = (unsigned)(it >> 1) & 1u;
+            const int mt = tile / p.n_qtiles, qt = tile % p.n_qtiles;
+            bar_wait(&S.tfull[acc], aph);
+            tc_fence_after();
+            const long long m = (long long)mt * TC_M + quarter * 32 + lane;     // global output-row index n * H + p
+            const int n = (int)(m / p.H), pr = (int)(m % p.H);
+            const bool row_ok = n < p.n_img && pr < p.P;
+            const int q0 = qt * p.Qt;
+            int valid_cols = (p.Q - q0) * p.K;
+            if (valid_cols > p.ncols) valid_cols = p.ncols;
+            __nv_bfloat16 *yrow = p.y + ((long long)n * p.P + pr) * p.y_row_elems + (long long)q0 * p.K;
+            for (int c0 = 0; c0 < p.ncols; c0 += 32) {
+                uint32_t v[32];
+                tc_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (c0 + j >= valid_cols) break;
+                        float f[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            f[u] = __uint_as_float(v[j + u]) + S.bias[c0 + j + u];
+                            if (p.act == 1) f[u] = __fdividef(1.0f, 1.0f + __expf(-f[u]));
+                        }
+                        if (c0 + j + 8 <= valid_cols && ((reinterpret_cast<uintptr_t>(yrow + c0 + j) & 15) == 0)) {
+                            uint4 o;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+                            o.x = *reinterpret_cast<uint32_t *>(&t0); o.y = *reinterpret_cast<uint32_t *>(&t1);
+                            o.z = *reinterpret_cast<uint32_t *>(&t2); o.w = *reinterpret_cast<uint32_t *>(&t3);
+                            *reinterpret_cast<uint4 *>(yrow + c0 + j) = o;
+                        } else {
+                            for (int u = 0; u < 8 && c0 + j + u < valid_cols; ++u) yrow[c0 + j + u] = __float2bfloat16_rn(f[u]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(&S.tempty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    }
+}
+
+// fp32 [rows][w] -> bf16 [rows][pitch] (zero padded), for building the padded NHWC activations the TMA map needs
+__global__ void k_f32_to_bf16_rows(const float *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long rows, int w, int pitch) {
+    const long total = rows * pitch;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / pitch;
+        const int c = (int)(i % pitch);
+        dst[i] = __float2bfloat16_rn(c < w ? src[r * w + c] : 0.0f);
+    }
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode(encode_tiled_fn *out) {
+    static encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+            pcnn_set_error("cuTensorMapEncodeTiled not available from the driver (%d)", (int)e);
+            return PCNN_ERR_CUDA;
+        }
+        fn = (encode_tiled_fn)p;
+    }
+    *out = fn;
+    return PCNN_OK;
+}
+
+int make_map_2d(CUtensorMap *map, void *base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer) {
+    encode_tiled_fn enc;
+    int rc = get_encode(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pcnn_set_error("cuTensorMapEncodeTiled failed (%d) for [%llu x %llu] pitch %llu box [%u x %u]", (int)r,
+                       (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_bytes, box_inner, box_outer);
+        return PCNN_ERR_CUDA;
+    }
+    return PCNN_OK;
+}
+
+uint16_t f32_to_bf16_bits(float f) {   // round to nearest even, as __float2bfloat16_rn
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+}  // namespace
+
+struct pcnn_conv_plan {
+    ConvTcParams p;
+    int W, S, row_pitch;
+    void *d_toeplitz = nullptr;     // [R][ncols][32] bf16
+    float *d_bias = nullptr;
+    CUtensorMap map_b;
+};
+
+extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int C, int K, int R, int S, int row_pitch,
+                                        int act, const float *filt_host, const float *bias_host, pcnn_conv_plan **out) {
+    PCNN_REQUIRE(ctx && filt_host && out, PCNN_ERR_ARG, "pcnn_conv_tc_plan_create: NULL argument");
+    PCNN_REQUIRE(N > 0 && H >= R && W >= S && C > 0 && K > 0 && R > 0 && R <= TC_MAX_R && S > 0, PCNN_ERR_ARG,
+                 "pcnn_conv_tc_plan_create: bad shape N=%d H=%d W=%d C=%d K=%d R=%d S=%d", N, H, W, C, K, R, S);
+    PCNN_REQUIRE(row_pitch >= W * C && row_pitch % 8 == 0, PCNN_ERR_ARG,
+                 "pcnn_conv_tc_plan_create: row pitch %d must be >= W*C and a multiple of 8 elements (TMA 16-byte strides)", row_pitch);
+    const int Q = W - S + 1, P = H - R + 1;
+    int Qt = 0;
+    for (int t = Q; t >= 1; --t)
+        if ((t + S - 1) * C <= TC_KCHUNK && t * K <= 256 && (t * K) % 16 == 0) { Qt = t; break; }
+    PCNN_REQUIRE(Qt > 0, PCNN_ERR_ARG, "pcnn_conv_tc_plan_create: no pixel block with (Qt+S-1)*C <= 32 and Qt*K <= 256, %%16 == 0");
+    pcnn_device_guard g(ctx->device);
+    pcnn_conv_plan *pl = new pcnn_conv_plan();
+    pl->W = W; pl->S = S; pl->row_pitch = row_pitch;
+    ConvTcParams &p = pl->p;
+    p.n_img = N; p.H = H; p.P = P; p.Q = Q; p.K = K; p.R = R; p.Qt = Qt; p.ncols = Qt * K; p.C = C;
+    p.n_mtiles = (int)(((long long)N * H + TC_M - 1) / TC_M);
+    p.n_qtiles = (Q + Qt - 1) / Qt;
+    p.act = act;
+    p.y_row_elems = (long long)Q * K;
+    // Toeplitz operand: T_r[(ql, k)][kk] = f[k][r][s][c] where kk = (ql + s) * C + c
+    std::vector<uint16_t> t((size_t)R * p.ncols * TC_KCHUNK, 0);
+    for (int r = 0; r < R; ++r)
+        for (int ql = 0; ql < Qt; ++ql)
+            for (int k = 0; k < K; ++k)
+                for (int s = 0; s < S; ++s)
+                    for (int c = 0; c < C; ++c)
+                        t[((size_t)r * p.ncols + ql * K + k) * TC_KCHUNK + (ql + s) * C + c] =
+                            f32_to_bf16_bits(filt_host[(((size_t)k * R + r) * S + s) * C + c]);
+    PCNN_CUDA(cudaMalloc(&pl->d_toeplitz, t.size() * 2));
+    PCNN_CUDA(cudaMemcpy(pl->d_toeplitz, t.data(), t.size() * 2, cudaMemcpyHostToDevice));
+    if (bias_host) {
+        PCNN_CUDA(cudaMalloc((void **)&pl->d_bias, K * sizeof(float)));
+        PCNN_CUDA(cudaMemcpy(pl->d_bias, bias_host, K * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    p.bias = pl->d_bias;
+    int rc = make_map_2d(&pl->map_b, pl->d_toeplitz, TC_KCHUNK, (uint64_t)R * p.ncols, TC_KCHUNK * 2, TC_KCHUNK, (uint32_t)p.ncols);
+    if (rc) { delete pl; return rc; }
+    static bool configured = false;
+    if (!configured) {
+        PCNN_CUDA(cudaFuncSetAttribute(k_conv_tc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvTcSmem) + 1024));
+        configured = true;
+    }
+    *out = pl;
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_conv_tc_plan_destroy(pcnn_ctx *ctx, pcnn_conv_plan *plan) {
+    PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_conv_tc_plan_destroy: ctx is NULL");
+    if (!plan) return PCNN_OK;
+    pcnn_device_guard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (plan->d_toeplitz) cudaFree(plan->d_toeplitz);
+    if (plan->d_bias) cudaFree(plan->d_bias);
+    delete plan;
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_conv_tc_fwd(pcnn_ctx *ctx, pcnn_conv_plan *plan, const void *x_bf16, void *y_bf16) {
+    PCNN_REQUIRE(ctx && plan && x_bf16 && y_bf16, PCNN_ERR_ARG, "pcnn_conv_tc_fwd: NULL argument");
+    PCNN_REQUIRE(((uintptr_t)x_bf16 & 15) == 0, PCNN_ERR_ARG, "pcnn_conv_tc_fwd: activations must be 16-byte aligned");
+    pcnn_device_guard g(ctx->device);
+    ConvTcParams p = plan->p;
+    p.y = reinterpret_cast<__nv_bfloat16 *>(y_bf16);
+    CUtensorMap map_x;
+    int rc = make_map_2d(&map_x, const_cast<void *>(x_bf16), (uint64_t)plan->row_pitch, (uint64_t)p.n_img * p.H,
+                         (uint64_t)plan->row_pitch * 2, TC_KCHUNK, TC_M);
+    if (rc) return rc;
+    const int ntiles = p.n_mtiles * p.n_qtiles;
+    const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
+    k_conv_tc_fwd<<<grid, TC_THREADS, sizeof(ConvTcSmem) + 1024, ctx->stream>>>(map_x, plan->map_b, p);
+    PCNN_CHECK_LAUNCH(ctx);
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_f32_to_bf16_rows(pcnn_ctx *ctx, const float *src, void *dst_bf16, long rows, int w, int pitch) {
+    PCNN_REQUIRE(ctx && src && dst_bf16 && rows > 0 && w > 0 && pitch >= w, PCNN_ERR_ARG, "pcnn_f32_to_bf16_rows: bad argument");
+    pcnn_device_guard g(ctx->device);
+    long blocks = (rows * pitch + 255) / 256;
+    if (blocks > (long)ctx->sm_count * 16) blocks = (long)ctx->sm_count * 16;
+    k_f32_to_bf16_rows<<<(int)blocks, 256, 0, ctx->stream>>>(src, reinterpret_cast<__nv_bfloat16 *>(dst_bf16), rows, w, pitch);
+    PCNN_CHECK_LAUNCH(ctx);
+    return PCNN_OK;
+}

@@ -336,4 +336,48 @@ class Engine:
         self._call("pcnn_softmax_ce", _p(logits), _p(labels), int(B), int(n), _p(prob), _p(d), _p(loss))
 
 
-__all__ = ["Engine", "DeviceArray", "TRAIN_SET", "TEST_SET", "U8", "F32"]
+class ConvPlan:
+    """bf16 tensor-core convolution plan (pcnn_conv_tc_*): filters fp32 KRSC on the host, activations NHWC bf16."""
+
+    def __init__(self, engine, N, H, W, C, K, R, S, filt, bias=None, act=0, row_pitch=None):
+        self.engine = engine
+        self.shape = (N, H, W, C, K, R, S)
+        self.row_pitch = int(row_pitch if row_pitch is not None else (W * C + 7) // 8 * 8)
+        filt = np.ascontiguousarray(filt, np.float32)
+        assert filt.size == K * R * S * C
+        b = None if bias is None else np.ascontiguousarray(bias, np.float32)
+        plan = C_.c_void_p()
+        check("pcnn_conv_tc_plan_create",
+              lib().pcnn_conv_tc_plan_create(engine.ctx, N, H, W, C, K, R, S, self.row_pitch, int(act), filt.ctypes.data,
+                                             None if b is None else b.ctypes.data, C_.byref(plan)))
+        self.plan = plan
+        self.out_shape = (N, H - R + 1, W - S + 1, K)
+
+    def fwd(self, x_bf16_dev, y_bf16_dev):
+        check("pcnn_conv_tc_fwd", lib().pcnn_conv_tc_fwd(self.engine.ctx, self.plan, _p(x_bf16_dev), _p(y_bf16_dev)))
+
+    def close(self):
+        if self.plan and self.engine.ctx:
+            lib().pcnn_conv_tc_plan_destroy(self.engine.ctx, self.plan)
+        self.plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def f32_to_bf16_bits(a):
+    """numpy float32 -> uint16 bf16 bit patterns (round to nearest even), the rounding the kernels use"""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    u = u + 0x7FFF + ((u >> 16) & 1)
+    return (u >> 16).astype(np.uint16)
+
+
+def bf16_bits_to_f32(b):
+    return (np.ascontiguousarray(b, np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+C_ = C
+__all__ = ["Engine", "DeviceArray", "ConvPlan", "f32_to_bf16_bits", "bf16_bits_to_f32", "TRAIN_SET", "TEST_SET", "U8", "F32"]

@@ -1,0 +1,91 @@
+"""GPU parity tests of the bf16 tcgen05 convolution (csrc/conv_tc.cu).
+
+PARITY UNPINNED by the reference (no bf16 / tensor-core path exists there).  The checker is the direct convolution
+orc_conv_fwd_nhwc (oracle/lenet_oracle.c: the reference's conv semantics, layer.h:118-130, generalised to C channels and
+K filters, double accumulation) evaluated on the SAME bf16-rounded activations and filters, so the only differences are
+fp32 accumulation order in the tensor core and the final bf16 rounding of the output:
+    |d| <= 2^-8 |ref| + 1e-3   per element,   rel-L2 <= 4e-3     (stated bound of SURVEY.md 8c item 5: 2e-2)
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def conv_case(eng, pkg, N, H, W, C, K, R, S, act, seed, real=None):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, (N, H, W, C)).astype(np.float32) if real is None else real        # config 5: x ~ U[0,1)
+    f = rng.uniform(-0.5, 0.5, (K, R, S, C)).astype(np.float32)                                # same law as layer.h:49-52
+    b = rng.uniform(-0.5, 0.5, K).astype(np.float32)
+    xb = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(x))
+    fb = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(f))
+    P, Q = H - R + 1, W - S + 1
+    ref = np.empty((N, P, Q, K), np.float32)
+    O.oracle().orc_conv_fwd_nhwc(O.fp(xb.reshape(-1)), O.fp(fb.reshape(-1)), O.fp(b), O.fp(ref.reshape(-1)), N, H, W, C, K, R, S)
+    if act:
+        ref = (1.0 / (1.0 + np.exp(-ref.astype(np.float64)))).astype(np.float32)
+    pitch = (W * C + 7) // 8 * 8
+    xp = np.zeros((N * H, pitch), np.uint16)
+    xp[:, : W * C] = pkg.f32_to_bf16_bits(x).reshape(N * H, W * C)
+    plan = pkg.ConvPlan(eng, N, H, W, C, K, R, S, fb, b, act=act, row_pitch=pitch)
+    dx = eng.to_device(xp)
+    dy = eng.array((N, P, Q, K), np.uint16)
+    plan.fwd(dx, dy)
+    eng.sync()
+    got = pkg.bf16_bits_to_f32(dy.to_host())
+    plan.close()
+    err = np.abs(got - ref)
+    assert np.all(err <= 2.0 ** -8 * np.abs(ref) + 1e-3), (float(err.max()), np.unravel_index(err.argmax(), err.shape))
+    rel = np.linalg.norm((got - ref).astype(np.float64)) / np.linalg.norm(ref.astype(np.float64))
+    assert rel <= 4e-3, rel
+    return rel
+
+
+def test_lenet_c1_shape_random(eng, pkg):
+    # config 3 shape: 28x28x1 -> 6 filters 5x5, 128 images (4 full row-tiles of 128 rows = 28 tiles)
+    conv_case(eng, pkg, 128, 28, 28, 1, 6, 5, 5, act=0, seed=1)
+
+
+def test_lenet_c1_real_digits_with_sigmoid_epilogue(eng, pkg, golden):
+    # the c1 layer of the reference on real MNIST digits with the seed-1 filters, bias + sigmoid fused: compare with
+    # the fp32 oracle's c1.output (layer.h:105-140 + :85-89) at bf16 resolution
+    N = 64
+    imgs = O.u8_to_f32(golden["train_u8"][:N]).reshape(N, 28, 28, 1)
+    p = golden["params_init"]
+    filt = p[0:150].reshape(6, 5, 5, 1)
+    bias = p[150:156]
+    pitch = 32
+    xp = np.zeros((N * 28, pitch), np.uint16)
+    xp[:, :28] = pkg.f32_to_bf16_bits(imgs).reshape(N * 28, 28)
+    plan = pkg.ConvPlan(eng, N, 28, 28, 1, 6, 5, 5, filt, bias, act=1, row_pitch=pitch)
+    dy = eng.array((N, 24, 24, 6), np.uint16)
+    plan.fwd(eng.to_device(xp), dy)
+    eng.sync()
+    got = pkg.bf16_bits_to_f32(dy.to_host())                       # NHWC
+    plan.close()
+    ref = np.stack([O.forward(p, imgs[s].reshape(-1))[3456:6912].reshape(6, 24, 24) for s in range(N)])   # NCHW fp32
+    ref = ref.transpose(0, 2, 3, 1)
+    # bf16 inputs/filters (2^-9 relative each) through a 25-term sum and a sigmoid: 2e-2 rel-L2 is SURVEY.md's stated bound
+    rel = np.linalg.norm((got - ref).astype(np.float64)) / np.linalg.norm(ref.astype(np.float64))
+    assert rel <= 2e-2, rel
+    assert np.abs(got - ref).max() <= 3e-2
+
+
+@pytest.mark.parametrize("N,H,W", [(1, 224, 224), (2, 64, 40), (3, 19, 23)])
+def test_config5_shape(eng, pkg, N, H, W):
+    # 3 input channels, 64 filters of 3x3: pixel blocks of 4, ragged last block (222 = 55 * 4 + 2), ragged row tiles
+    conv_case(eng, pkg, N, H, W, 3, 64, 3, 3, act=0, seed=N * 100 + H)
+
+
+def test_other_small_channel_shapes(eng, pkg):
+    conv_case(eng, pkg, 5, 12, 30, 2, 16, 3, 5, act=0, seed=9)      # C = 2, K = 16, 3x5 taps
+    conv_case(eng, pkg, 2, 33, 33, 4, 32, 5, 3, act=1, seed=10)     # C = 4, K = 32, 5x3 taps, sigmoid epilogue
+
+
+def test_plan_rejects_unsupported_shapes(eng, pkg):
+    with pytest.raises(pkg.PcnnError):
+        pkg.ConvPlan(eng, 1, 32, 32, 64, 64, 3, 3, np.zeros(64 * 9 * 64, np.float32))      # (Qt+S-1)*C > 32 for every Qt
+    with pytest.raises(pkg.PcnnError):
+        pkg.ConvPlan(eng, 1, 28, 28, 1, 6, 5, 5, np.zeros(150, np.float32), row_pitch=28)   # pitch not a multiple of 8
