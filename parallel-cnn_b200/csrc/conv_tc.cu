@@ -33,7 +33,8 @@ namespace {
 constexpr int TC_THREADS = 192;
 constexpr int TC_M = 128;          // output rows per tile (TMEM lanes)
 constexpr int TC_KCHUNK = 32;      // bf16 elements per filter row r (64 B = one SWIZZLE_64B span)
-constexpr int TC_STAGES = 3;
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_SMEM_BUDGET = 220 * 1024;
 constexpr int TC_MAX_R = 5;
 constexpr int A_TILE_BYTES = TC_M * TC_KCHUNK * 2;   // 8 KB
 
@@ -41,6 +42,9 @@ struct ConvTcParams {
     int n_img, H, P, Q, K, R;      // images, input rows per image, valid output rows/cols, filters, filter rows
     int Qt, ncols;                 // output pixels per tile, Qt * K
     int C;                         // input channels (column offset of a tile = q0 * C elements)
+    int V;                         // Toeplitz variants: the box start is rounded down to 8 elements (16 B, a TMA
+                                   // requirement on the global address), the remainder (q0*C) % 8 selects the variant
+    int stages;                    // activation stages that fit next to the V * R Toeplitz matrices
     int n_mtiles, n_qtiles;
     int act;                       // 0: none, 1: sigmoid (the reference's activation, layer.h:81-83)
     long long y_row_elems;         // Q * K
@@ -119,23 +123,40 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-struct alignas(1024) ConvTcSmem {
-    unsigned char a[TC_STAGES][TC_MAX_R][A_TILE_BYTES];   // 3 x 5 x 8 KB = 120 KB
-    unsigned char b[TC_MAX_R][256 * TC_KCHUNK * 2];       // 5 x 16 KB = 80 KB
+// dynamic shared memory, 1024-byte aligned:  [V*R Toeplitz matrices of ncols*64 B] [stages*R activation tiles of 8 KB] [ctl]
+struct ConvTcCtl {
     float bias[256];
-    unsigned long long full[TC_STAGES], empty[TC_STAGES], tfull[2], tempty[2], bfull;
+    unsigned long long full[TC_MAX_STAGES], empty[TC_MAX_STAGES], tfull[2], tempty[2], bfull;
     uint32_t tmem_base;
 };
+struct ConvTcSmemView {
+    unsigned char *base;
+    int R, bmat, stages, V;
+    __device__ __forceinline__ unsigned char *b(int v, int r) const { return base + (size_t)(v * R + r) * bmat; }
+    __device__ __forceinline__ unsigned char *a(int stage, int r) const {
+        return base + (size_t)V * R * bmat + (size_t)(stage * R + r) * A_TILE_BYTES;
+    }
+    __device__ __forceinline__ ConvTcCtl &ctl() const {
+        return *reinterpret_cast<ConvTcCtl *>(base + (size_t)V * R * bmat + (size_t)stages * R * A_TILE_BYTES);
+    }
+};
+static size_t conv_tc_smem_bytes(int V, int R, int ncols, int stages) {
+    return (size_t)V * R * ncols * TC_KCHUNK * 2 + (size_t)stages * R * A_TILE_BYTES + sizeof(ConvTcCtl) + 1024;
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const ConvTcParams p) {
     extern __shared__ unsigned char smem_dyn[];
-    ConvTcSmem &S = *reinterpret_cast<ConvTcSmem *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    ConvTcSmemView sv;
+    sv.base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    sv.R = p.R; sv.bmat = p.ncols * TC_KCHUNK * 2; sv.stages = p.stages; sv.V = p.V;
+    ConvTcCtl &S = sv.ctl();
+    const int NST = p.stages;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = p.n_mtiles * p.n_qtiles;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_STAGES; ++i) { bar_init(&S.full[i], 1); bar_init(&S.empty[i], 1); }
+        for (int i = 0; i < NST; ++i) { bar_init(&S.full[i], 1); bar_init(&S.empty[i], 1); }
         for (int i = 0; i < 2; ++i) { bar_init(&S.tfull[i], 1); bar_init(&S.tempty[i], 4); }
         bar_init(&S.bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -153,17 +174,18 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     if (warp == 0) {
         // ===== TMA producer: the Toeplitz operand once, then R activation boxes per tile =====
         if (lane == 0) {
-            bar_expect_tx(&S.bfull, (unsigned)(p.R * p.ncols * TC_KCHUNK * 2));
-            for (int r = 0; r < p.R; ++r) tma_load_2d(S.b[r], &map_b, 0, r * p.ncols, &S.bfull);
+            bar_expect_tx(&S.bfull, (unsigned)(p.V * p.R * p.ncols * TC_KCHUNK * 2));
+            for (int v = 0; v < p.V; ++v)
+                for (int r = 0; r < p.R; ++r) tma_load_2d(sv.b(v, r), &map_b, 0, (v * p.R + r) * p.ncols, &S.bfull);
             int it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int stage = it % TC_STAGES;
-                const unsigned ph = (unsigned)(it / TC_STAGES) & 1u;
+                const int stage = it % NST;
+                const unsigned ph = (unsigned)(it / NST) & 1u;
                 bar_wait(&S.empty[stage], ph ^ 1u);
                 const int mt = tile / p.n_qtiles, qt = tile % p.n_qtiles;
                 bar_expect_tx(&S.full[stage], (unsigned)(p.R * A_TILE_BYTES));
                 for (int r = 0; r < p.R; ++r)
-                    tma_load_2d(S.a[stage][r], &map_x, qt * p.Qt * p.C, mt * TC_M + r, &S.full[stage]);
+                    tma_load_2d(sv.a(stage, r), &map_x, (qt * p.Qt * p.C) & ~7, mt * TC_M + r, &S.full[stage]);
             }
         }
     } else if (warp == 1) {
@@ -173,16 +195,17 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             bar_wait(&S.bfull, 0);
             int it = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int stage = it % TC_STAGES;
-                const unsigned ph = (unsigned)(it / TC_STAGES) & 1u;
+                const int stage = it % NST;
+                const unsigned ph = (unsigned)(it / NST) & 1u;
                 const int acc = it & 1;
                 const unsigned aph = (unsigned)(it >> 1) & 1u;
                 bar_wait(&S.tempty[acc], aph ^ 1u);            // epilogue has drained this accumulator
                 bar_wait(&S.full[stage], ph);                   // activations have landed
                 tc_fence_after();
                 const uint32_t d = tmem + (uint32_t)(acc * 256);
+                const int var = (tile % p.n_qtiles) % p.V;      // which 16-byte remainder this pixel block starts at
                 for (int r = 0; r < p.R; ++r) {
-                    const uint32_t a0 = s_u32(S.a[stage][r]), b0 = s_u32(S.b[r]);
+                    const uint32_t a0 = s_u32(sv.a(stage, r)), b0 = s_u32(sv.b(var, r));
 #pragma unroll
                     for (int ks = 0; ks < TC_KCHUNK / 16; ++ks)   // K = 16 bf16 = 32 bytes per instruction
                         tc_mma_bf16(d, umma_desc_k_sw64(a0 + ks * 32), umma_desc_k_sw64(b0 + ks * 32), idesc,
@@ -322,28 +345,46 @@ extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int 
     PCNN_REQUIRE(row_pitch >= W * C && row_pitch % 8 == 0, PCNN_ERR_ARG,
                  "pcnn_conv_tc_plan_create: row pitch %d must be >= W*C and a multiple of 8 elements (TMA 16-byte strides)", row_pitch);
     const int Q = W - S + 1, P = H - R + 1;
-    int Qt = 0;
-    for (int t = Q; t >= 1; --t)
-        if ((t + S - 1) * C <= TC_KCHUNK && t * K <= 256 && (t * K) % 16 == 0) { Qt = t; break; }
-    PCNN_REQUIRE(Qt > 0, PCNN_ERR_ARG, "pcnn_conv_tc_plan_create: no pixel block with (Qt+S-1)*C <= 32 and Qt*K <= 256, %%16 == 0");
+    // pixel block Qt: the TMA box must start on a 16-byte boundary, so it starts at (q0*C) & ~7 and the Toeplitz
+    // operand absorbs the remainder delta = (q0*C) % 8: delta + (Qt+S-1)*C elements must fit the 32-element K chunk.
+    // q0 = qt * Qt, so delta cycles with period V = 8 / gcd(8, Qt*C); each remainder needs its own operand copy.
+    auto gcd = [](int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; };
+    int Qt = 0, V = 1, stages = 0;
+    for (int t = Q; t >= 1 && !Qt; --t) {
+        if (t * K > 256 || (t * K) % 16 != 0) continue;
+        const int single = ((Q + t - 1) / t) == 1;                       // one block per row: delta is always 0
+        const int v = single ? 1 : 8 / gcd(8, (t * C) % 8 == 0 ? 8 : (t * C) % 8);
+        int max_delta = 0;
+        for (int i = 0; i < v; ++i) max_delta = max_delta > (i * t * C) % 8 ? max_delta : (i * t * C) % 8;
+        if (max_delta + (t + S - 1) * C > TC_KCHUNK) continue;
+        const size_t fixed = (size_t)v * R * t * K * TC_KCHUNK * 2 + sizeof(ConvTcCtl) + 1024;
+        if (fixed + 2 * (size_t)R * A_TILE_BYTES > (size_t)TC_SMEM_BUDGET) continue;
+        int st = (int)(((size_t)TC_SMEM_BUDGET - fixed) / ((size_t)R * A_TILE_BYTES));
+        Qt = t; V = v; stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
+    }
+    PCNN_REQUIRE(Qt > 0, PCNN_ERR_ARG,
+                 "pcnn_conv_tc_plan_create: no pixel block with (Qt+S-1)*C (+ alignment remainder) <= 32, Qt*K <= 256, %%16 == 0");
     pcnn_device_guard g(ctx->device);
     pcnn_conv_plan *pl = new pcnn_conv_plan();
     pl->W = W; pl->S = S; pl->row_pitch = row_pitch;
     ConvTcParams &p = pl->p;
-    p.n_img = N; p.H = H; p.P = P; p.Q = Q; p.K = K; p.R = R; p.Qt = Qt; p.ncols = Qt * K; p.C = C;
+    p.n_img = N; p.H = H; p.P = P; p.Q = Q; p.K = K; p.R = R; p.Qt = Qt; p.ncols = Qt * K; p.C = C; p.V = V; p.stages = stages;
     p.n_mtiles = (int)(((long long)N * H + TC_M - 1) / TC_M);
     p.n_qtiles = (Q + Qt - 1) / Qt;
     p.act = act;
     p.y_row_elems = (long long)Q * K;
-    // Toeplitz operand: T_r[(ql, k)][kk] = f[k][r][s][c] where kk = (ql + s) * C + c
-    std::vector<uint16_t> t((size_t)R * p.ncols * TC_KCHUNK, 0);
-    for (int r = 0; r < R; ++r)
-        for (int ql = 0; ql < Qt; ++ql)
-            for (int k = 0; k < K; ++k)
-                for (int s = 0; s < S; ++s)
-                    for (int c = 0; c < C; ++c)
-                        t[((size_t)r * p.ncols + ql * K + k) * TC_KCHUNK + (ql + s) * C + c] =
-                            f32_to_bf16_bits(filt_host[(((size_t)k * R + r) * S + s) * C + c]);
+    // Toeplitz operands: T_{v,r}[(ql, k)][kk] = f[k][r][s][c] where kk = delta_v + (ql + s) * C + c
+    std::vector<uint16_t> t((size_t)V * R * p.ncols * TC_KCHUNK, 0);
+    for (int v = 0; v < V; ++v) {
+        const int delta = (v * Qt * C) % 8;
+        for (int r = 0; r < R; ++r)
+            for (int ql = 0; ql < Qt; ++ql)
+                for (int k = 0; k < K; ++k)
+                    for (int s = 0; s < S; ++s)
+                        for (int c = 0; c < C; ++c)
+                            t[(((size_t)v * R + r) * p.ncols + ql * K + k) * TC_KCHUNK + delta + (ql + s) * C + c] =
+                                f32_to_bf16_bits(filt_host[(((size_t)k * R + r) * S + s) * C + c]);
+    }
     PCNN_CUDA(cudaMalloc(&pl->d_toeplitz, t.size() * 2));
     PCNN_CUDA(cudaMemcpy(pl->d_toeplitz, t.data(), t.size() * 2, cudaMemcpyHostToDevice));
     if (bias_host) {
@@ -351,11 +392,11 @@ extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int 
         PCNN_CUDA(cudaMemcpy(pl->d_bias, bias_host, K * sizeof(float), cudaMemcpyHostToDevice));
     }
     p.bias = pl->d_bias;
-    int rc = make_map_2d(&pl->map_b, pl->d_toeplitz, TC_KCHUNK, (uint64_t)R * p.ncols, TC_KCHUNK * 2, TC_KCHUNK, (uint32_t)p.ncols);
+    int rc = make_map_2d(&pl->map_b, pl->d_toeplitz, TC_KCHUNK, (uint64_t)V * R * p.ncols, TC_KCHUNK * 2, TC_KCHUNK, (uint32_t)p.ncols);
     if (rc) { delete pl; return rc; }
     static bool configured = false;
     if (!configured) {
-        PCNN_CUDA(cudaFuncSetAttribute(k_conv_tc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ConvTcSmem) + 1024));
+        PCNN_CUDA(cudaFuncSetAttribute(k_conv_tc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
         configured = true;
     }
     *out = pl;
@@ -385,7 +426,7 @@ extern "C" int pcnn_conv_tc_fwd(pcnn_ctx *ctx, pcnn_conv_plan *plan, const void 
     if (rc) return rc;
     const int ntiles = p.n_mtiles * p.n_qtiles;
     const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
-    k_conv_tc_fwd<<<grid, TC_THREADS, sizeof(ConvTcSmem) + 1024, ctx->stream>>>(map_x, plan->map_b, p);
+    k_conv_tc_fwd<<<grid, TC_THREADS, conv_tc_smem_bytes(p.V, p.R, p.ncols, p.stages), ctx->stream>>>(map_x, plan->map_b, p);
     PCNN_CHECK_LAUNCH(ctx);
     return PCNN_OK;
 }
