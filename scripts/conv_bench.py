@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""scripts/conv_bench.py -- throughput of the bf16 tcgen05 convolution forward (BASELINE.json configs 3 and 5) against the
+HBM roofline.  Algorithmic bytes per image are SURVEY.md 8d's: each operand crosses HBM once (input read + output written,
+bf16): LeNet c1 8,480 B, 224x224x3 -> 64 x 3x3: 6,609,408 B.  CUDA-event timing over back-to-back launches after warm-up;
+the working set of every measured point except the smallest batches exceeds the 126 MB L2."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import pcnn_loader  # noqa: E402
+
+pkg = pcnn_loader.load()
+torch.cuda.set_device(0)
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+eng = pkg.Engine(0, stream.cuda_stream)
+HBM = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+rng = np.random.default_rng(1234)
+only = sys.argv[1] if len(sys.argv) > 1 else "all"
+
+
+def run(name, N, H, W, C, K, R, S, act, iters):
+    pitch = (W * C + 7) // 8 * 8
+    P, Q = H - R + 1, W - S + 1
+    f = rng.uniform(-0.5, 0.5, (K, R, S, C)).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, K).astype(np.float32)
+    plan = pkg.ConvPlan(eng, N, H, W, C, K, R, S, f, b, act=act, row_pitch=pitch)
+    x = torch.randint(0, 0x3F80, (N * H, pitch), dtype=torch.int16, device="cuda")       # positive bf16 bit patterns < 1.0
+    y = torch.empty((N, P, Q, K), dtype=torch.int16, device="cuda")
+    for _ in range(3):
+        plan.fwd(x, y)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(iters):
+        plan.fwd(x, y)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    alg = N * (H * W * C + P * Q * K) * 2                       # bf16 in + out, once each
+    flops = 2.0 * N * P * Q * K * R * S * C
+    row = {"case": name, "N": N, "ms": ms, "img_per_s": N / (ms * 1e-3), "alg_GBps": alg / (ms * 1e-3) / 1e9,
+           "hbm_frac": alg / (ms * 1e-3) / 1e9 / HBM, "useful_TFLOPs": flops / (ms * 1e-3) / 1e12,
+           "working_set_MB": (N * H * pitch + N * P * Q * K) * 2 / 1e6}
+    print(json.dumps(row), flush=True)
+    plan.close()
+    del x, y
+
+
+if only in ("all", "lenet"):
+    for N in (1024, 8192, 65536):
+        run("lenet_c1_bf16_sigmoid (config 3 shape)", N, 28, 28, 1, 6, 5, 5, 1, 20)
+if only in ("all", "cfg5"):
+    for N in (1, 8, 32, 128):
+        run("224x224x3->64x3x3 bf16 (config 5)", N, 224, 224, 3, 64, 3, 3, 0, 10)
+eng.close()
