@@ -37,6 +37,7 @@ constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_SMEM_BUDGET = 220 * 1024;
 constexpr int TC_MAX_R = 5;
 constexpr int A_TILE_BYTES = TC_M * TC_KCHUNK * 2;   // 8 KB
+constexpr int OUT_STAGE_BYTES = 32 * 512;            // one epilogue warp's 32 output rows of up to 256 bf16
 
 struct ConvTcParams {
     int n_img, H, P, Q, K, R;      // images, input rows per image, valid output rows/cols, filters, filter rows
@@ -136,12 +137,15 @@ struct ConvTcSmemView {
     __device__ __forceinline__ unsigned char *a(int stage, int r) const {
         return base + (size_t)V * R * bmat + (size_t)(stage * R + r) * A_TILE_BYTES;
     }
+    __device__ __forceinline__ unsigned char *out(int epi_warp) const {      // 32 rows x 512 B per epilogue warp
+        return base + (size_t)V * R * bmat + (size_t)stages * R * A_TILE_BYTES + (size_t)epi_warp * OUT_STAGE_BYTES;
+    }
     __device__ __forceinline__ ConvTcCtl &ctl() const {
-        return *reinterpret_cast<ConvTcCtl *>(base + (size_t)V * R * bmat + (size_t)stages * R * A_TILE_BYTES);
+        return *reinterpret_cast<ConvTcCtl *>(base + (size_t)V * R * bmat + (size_t)stages * R * A_TILE_BYTES + 4 * OUT_STAGE_BYTES);
     }
 };
 static size_t conv_tc_smem_bytes(int V, int R, int ncols, int stages) {
-    return (size_t)V * R * ncols * TC_KCHUNK * 2 + (size_t)stages * R * A_TILE_BYTES + sizeof(ConvTcCtl) + 1024;
+    return (size_t)V * R * ncols * TC_KCHUNK * 2 + (size_t)stages * R * A_TILE_BYTES + 4 * OUT_STAGE_BYTES + sizeof(ConvTcCtl) + 1024;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -216,8 +220,14 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             }
         }
     } else {
-        // ===== epilogue warps: TMEM -> registers -> bias / activation -> bf16 -> global =====
+        // ===== epilogue warps: TMEM -> registers -> bias / activation -> bf16 -> swizzled smem -> coalesced global =====
+        // A TMEM lane is an output row, so one tcgen05.ld hands every thread 32 columns of ITS row; storing those
+        // directly makes each store instruction touch 32 different rows (16 B per row).  Instead the warp parks its
+        // 32 rows x ncols bf16 in shared memory (16-byte chunk c of row r at slot c ^ r: conflict-free both ways) and
+        // writes every row out with one fully coalesced instruction (32 lanes x 16 B = 512 contiguous bytes).
         const int quarter = warp & 3;                           // TMEM lanes this warp may read
+        unsigned char *obuf = sv.out(warp - 2);
+        const int nchunks = p.ncols / 8;                        // 16-byte chunks per output row of the tile
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -225,42 +235,53 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             const int mt = tile / p.n_qtiles, qt = tile % p.n_qtiles;
             bar_wait(&S.tfull[acc], aph);
             tc_fence_after();
-            const long long m = (long long)mt * TC_M + quarter * 32 + lane;     // global output-row index n * H + p
-            const int n = (int)(m / p.H), pr = (int)(m % p.H);
-            const bool row_ok = n < p.n_img && pr < p.P;
             const int q0 = qt * p.Qt;
             int valid_cols = (p.Q - q0) * p.K;
             if (valid_cols > p.ncols) valid_cols = p.ncols;
-            __nv_bfloat16 *yrow = p.y + ((long long)n * p.P + pr) * p.y_row_elems + (long long)q0 * p.K;
             for (int c0 = 0; c0 < p.ncols; c0 += 32) {
                 uint32_t v[32];
                 tc_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
-                if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        if (c0 + j >= valid_cols) break;
+                for (int j = 0; j < 32; j += 8) {
+                    if (c0 + j < p.ncols) {
                         float f[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
                             f[u] = __uint_as_float(v[j + u]) + S.bias[c0 + j + u];
                             if (p.act == 1) f[u] = __fdividef(1.0f, 1.0f + __expf(-f[u]));
                         }
-                        if (c0 + j + 8 <= valid_cols && ((reinterpret_cast<uintptr_t>(yrow + c0 + j) & 15) == 0)) {
-                            uint4 o;
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
-                            o.x = *reinterpret_cast<uint32_t *>(&t0); o.y = *reinterpret_cast<uint32_t *>(&t1);
-                            o.z = *reinterpret_cast<uint32_t *>(&t2); o.w = *reinterpret_cast<uint32_t *>(&t3);
-                            *reinterpret_cast<uint4 *>(yrow + c0 + j) = o;
-                        } else {
-                            for (int u = 0; u < 8 && c0 + j + u < valid_cols; ++u) yrow[c0 + j + u] = __float2bfloat16_rn(f[u]);
-                        }
+                        uint4 o;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+                        o.x = *reinterpret_cast<uint32_t *>(&t0); o.y = *reinterpret_cast<uint32_t *>(&t1);
+                        o.z = *reinterpret_cast<uint32_t *>(&t2); o.w = *reinterpret_cast<uint32_t *>(&t3);
+                        const int chunk = (c0 + j) >> 3;
+                        *reinterpret_cast<uint4 *>(obuf + lane * 512 + ((chunk ^ lane) & 31) * 16) = o;
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) bar_arrive(&S.tempty[acc]);
+            if (lane == 0) bar_arrive(&S.tempty[acc]);          // accumulator drained: the next tile's MMAs may start
+            // write-out: row r of this warp's 32 rows per iteration, lane = 16-byte chunk of the row
+            long long m = (long long)mt * TC_M + quarter * 32;  // global output-row index n * H + p of row 0
+            int n = (int)(m / p.H), pr = (int)(m % p.H);
+            for (int r = 0; r < 32; ++r) {
+                if (n < p.n_img && pr < p.P) {
+                    __nv_bfloat16 *yrow = p.y + ((long long)n * p.P + pr) * p.y_row_elems + (long long)q0 * p.K;
+                    if (lane < nchunks && lane * 8 < valid_cols) {
+                        const uint4 o = *reinterpret_cast<const uint4 *>(obuf + r * 512 + ((lane ^ r) & 31) * 16);
+                        if (lane * 8 + 8 <= valid_cols && ((reinterpret_cast<uintptr_t>(yrow + lane * 8) & 15) == 0)) {
+                            *reinterpret_cast<uint4 *>(yrow + lane * 8) = o;
+                        } else {
+                            const __nv_bfloat16 *e = reinterpret_cast<const __nv_bfloat16 *>(&o);
+                            for (int u = 0; u < 8 && lane * 8 + u < valid_cols; ++u) yrow[lane * 8 + u] = e[u];
+                        }
+                    }
+                }
+                if (++pr == p.H) { pr = 0; ++n; }
+            }
+            __syncwarp();                                       // obuf is rewritten by the next tile
         }
     }
     tc_fence_before();
@@ -357,7 +378,7 @@ extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int 
         int max_delta = 0;
         for (int i = 0; i < v; ++i) max_delta = max_delta > (i * t * C) % 8 ? max_delta : (i * t * C) % 8;
         if (max_delta + (t + S - 1) * C > TC_KCHUNK) continue;
-        const size_t fixed = (size_t)v * R * t * K * TC_KCHUNK * 2 + sizeof(ConvTcCtl) + 1024;
+        const size_t fixed = (size_t)v * R * t * K * TC_KCHUNK * 2 + 4 * OUT_STAGE_BYTES + sizeof(ConvTcCtl) + 1024;
         if (fixed + 2 * (size_t)R * A_TILE_BYTES > (size_t)TC_SMEM_BUDGET) continue;
         int st = (int)(((size_t)TC_SMEM_BUDGET - fixed) / ((size_t)R * A_TILE_BYTES));
         Qt = t; V = v; stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
