@@ -37,7 +37,7 @@ constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_SMEM_BUDGET = 220 * 1024;
 constexpr int TC_MAX_R = 5;
 constexpr int A_TILE_BYTES = TC_M * TC_KCHUNK * 2;   // 8 KB
-constexpr int OUT_STAGE_BYTES = 32 * 512;            // one epilogue warp's 32 output rows of up to 256 bf16
+constexpr int OUT_STAGE_BYTES = 2 * 4096;            // per epilogue warp: two [32 rows x 64 cols] bf16 boxes for the TMA store
 
 struct ConvTcParams {
     int n_img, H, P, Q, K, R;      // images, input rows per image, valid output rows/cols, filters, filter rows
@@ -48,6 +48,7 @@ struct ConvTcParams {
     int stages;                    // activation stages that fit next to the V * R Toeplitz matrices
     int n_mtiles, n_qtiles;
     int act;                       // 0: none, 1: sigmoid (the reference's activation, layer.h:81-83)
+    int tma_store;                 // 1: epilogue writes y with cp.async.bulk.tensor stores (H % 32 == 0, 16-B row pitch)
     long long y_row_elems;         // Q * K
     __nv_bfloat16 *y;
     const float *bias;             // [K] or null
@@ -149,7 +150,8 @@ static size_t conv_tc_smem_bytes(int V, int R, int ncols, int stages) {
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const ConvTcParams p) {
+k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b,
+              const __grid_constant__ CUtensorMap map_y, const ConvTcParams p) {
     extern __shared__ unsigned char smem_dyn[];
     ConvTcSmemView sv;
     sv.base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -220,14 +222,16 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             }
         }
     } else {
-        // ===== epilogue warps: TMEM -> registers -> bias / activation -> bf16 -> swizzled smem -> coalesced global =====
-        // A TMEM lane is an output row, so one tcgen05.ld hands every thread 32 columns of ITS row; storing those
-        // directly makes each store instruction touch 32 different rows (16 B per row).  Instead the warp parks its
-        // 32 rows x ncols bf16 in shared memory (16-byte chunk c of row r at slot c ^ r: conflict-free both ways) and
-        // writes every row out with one fully coalesced instruction (32 lanes x 16 B = 512 contiguous bytes).
+        // ===== epilogue warps: TMEM -> registers -> bias / activation -> bf16 -> HBM =====
+        // A TMEM lane is an output row, so tcgen05.ld hands every thread 32 columns of ITS row.
+        //  * TMA-store path (image height a multiple of 32, 16-byte row pitch of y): the warp parks 32 rows x 64 columns
+        //    in shared memory in the SWIZZLE_128B pattern and one lane issues cp.async.bulk.tensor (a 3-D box
+        //    {64 cols, 32 rows, 1 image} of y): the store is asynchronous, rows p >= P and columns q >= Q fall outside the
+        //    tensor and are clipped by the hardware, and the warps go straight back to draining TMEM.
+        //  * direct path otherwise: 16-byte stores from registers (each lane its own row).
         const int quarter = warp & 3;                           // TMEM lanes this warp may read
-        unsigned char *obuf = sv.out(warp - 2);
-        const int nchunks = p.ncols / 8;                        // 16-byte chunks per output row of the tile
+        unsigned char *obuf = sv.out(warp - 2);                 // 2 x 4 KB, 1024-byte aligned
+        int ob = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -238,51 +242,86 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             const int q0 = qt * p.Qt;
             int valid_cols = (p.Q - q0) * p.K;
             if (valid_cols > p.ncols) valid_cols = p.ncols;
-            for (int c0 = 0; c0 < p.ncols; c0 += 32) {
-                uint32_t v[32];
-                tc_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+            if (p.tma_store) {
+                const long long m0 = (long long)mt * TC_M + quarter * 32;      // first row of this warp: n * H + p
+                const int n = (int)(m0 / p.H), pr = (int)(m0 % p.H);           // H % 32 == 0: the 32 rows share n
+                const bool group_ok = n < p.n_img && pr < p.P;
+                for (int col0 = 0; col0 < p.ncols; col0 += 64) {
+                    unsigned char *buf = obuf + ob * 4096;
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer `ob` is free again
+                    __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    if (c0 + j < p.ncols) {
-                        float f[8];
+                    for (int half = 0; half < 2; ++half) {
+                        const int c0 = col0 + half * 32;
+                        if (c0 < p.ncols) {
+                            uint32_t v[32];
+                            tc_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) {
-                            f[u] = __uint_as_float(v[j + u]) + S.bias[c0 + j + u];
-                            if (p.act == 1) f[u] = __fdividef(1.0f, 1.0f + __expf(-f[u]));
+                            for (int j = 0; j < 32; j += 8) {
+                                float f[8];
+#pragma unroll
+                                for (int u = 0; u < 8; ++u) {
+                                    f[u] = __uint_as_float(v[j + u]) + S.bias[c0 + j + u];
+                                    if (p.act == 1) f[u] = __fdividef(1.0f, 1.0f + __expf(-f[u]));
+                                }
+                                uint4 o;
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+                                o.x = *reinterpret_cast<uint32_t *>(&t0); o.y = *reinterpret_cast<uint32_t *>(&t1);
+                                o.z = *reinterpret_cast<uint32_t *>(&t2); o.w = *reinterpret_cast<uint32_t *>(&t3);
+                                const int chunk = half * 4 + (j >> 3);                     // 16-byte chunk of the 128-byte row
+                                *reinterpret_cast<uint4 *>(buf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+                            }
                         }
-                        uint4 o;
-                        __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
-                        __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
-                        o.x = *reinterpret_cast<uint32_t *>(&t0); o.y = *reinterpret_cast<uint32_t *>(&t1);
-                        o.z = *reinterpret_cast<uint32_t *>(&t2); o.w = *reinterpret_cast<uint32_t *>(&t3);
-                        const int chunk = (c0 + j) >> 3;
-                        *reinterpret_cast<uint4 *>(obuf + lane * 512 + ((chunk ^ lane) & 31) * 16) = o;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> TMA reads
+                    __syncwarp();
+                    if (lane == 0 && group_ok && col0 < valid_cols) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map_y),
+                                     "r"(q0 * p.K + col0), "r"(pr), "r"(n), "r"(s_u32(buf))
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ob ^= 1;
+                }
+            } else {
+                const long long m = (long long)mt * TC_M + quarter * 32 + lane;     // global output-row index n * H + p
+                const int n = (int)(m / p.H), pr = (int)(m % p.H);
+                const bool row_ok = n < p.n_img && pr < p.P;
+                __nv_bfloat16 *yrow = p.y + ((long long)n * p.P + pr) * p.y_row_elems + (long long)q0 * p.K;
+                for (int c0 = 0; c0 < p.ncols; c0 += 32) {
+                    uint32_t v[32];
+                    tc_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            if (c0 + j >= valid_cols) break;
+                            float f[8];
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                f[u] = __uint_as_float(v[j + u]) + S.bias[c0 + j + u];
+                                if (p.act == 1) f[u] = __fdividef(1.0f, 1.0f + __expf(-f[u]));
+                            }
+                            if (c0 + j + 8 <= valid_cols && ((reinterpret_cast<uintptr_t>(yrow + c0 + j) & 15) == 0)) {
+                                uint4 o;
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(f[4], f[5]), t3 = __floats2bfloat162_rn(f[6], f[7]);
+                                o.x = *reinterpret_cast<uint32_t *>(&t0); o.y = *reinterpret_cast<uint32_t *>(&t1);
+                                o.z = *reinterpret_cast<uint32_t *>(&t2); o.w = *reinterpret_cast<uint32_t *>(&t3);
+                                *reinterpret_cast<uint4 *>(yrow + c0 + j) = o;
+                            } else {
+                                for (int u = 0; u < 8 && c0 + j + u < valid_cols; ++u) yrow[c0 + j + u] = __float2bfloat16_rn(f[u]);
+                            }
+                        }
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) bar_arrive(&S.tempty[acc]);          // accumulator drained: the next tile's MMAs may start
-            // write-out: row r of this warp's 32 rows per iteration, lane = 16-byte chunk of the row
-            long long m = (long long)mt * TC_M + quarter * 32;  // global output-row index n * H + p of row 0
-            int n = (int)(m / p.H), pr = (int)(m % p.H);
-            for (int r = 0; r < 32; ++r) {
-                if (n < p.n_img && pr < p.P) {
-                    __nv_bfloat16 *yrow = p.y + ((long long)n * p.P + pr) * p.y_row_elems + (long long)q0 * p.K;
-                    if (lane < nchunks && lane * 8 < valid_cols) {
-                        const uint4 o = *reinterpret_cast<const uint4 *>(obuf + r * 512 + ((lane ^ r) & 31) * 16);
-                        if (lane * 8 + 8 <= valid_cols && ((reinterpret_cast<uintptr_t>(yrow + lane * 8) & 15) == 0)) {
-                            *reinterpret_cast<uint4 *>(yrow + lane * 8) = o;
-                        } else {
-                            const __nv_bfloat16 *e = reinterpret_cast<const __nv_bfloat16 *>(&o);
-                            for (int u = 0; u < 8 && lane * 8 + u < valid_cols; ++u) yrow[lane * 8 + u] = e[u];
-                        }
-                    }
-                }
-                if (++pr == p.H) { pr = 0; ++n; }
-            }
-            __syncwarp();                                       // obuf is rewritten by the next tile
+            if (lane == 0) bar_arrive(&S.tempty[acc]);
         }
+        if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed
+        __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
@@ -335,6 +374,24 @@ int make_map_2d(CUtensorMap *map, void *base, uint64_t inner, uint64_t outer, ui
     if (r != CUDA_SUCCESS) {
         pcnn_set_error("cuTensorMapEncodeTiled failed (%d) for [%llu x %llu] pitch %llu box [%u x %u]", (int)r,
                        (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_bytes, box_inner, box_outer);
+        return PCNN_ERR_CUDA;
+    }
+    return PCNN_OK;
+}
+
+// y viewed as [N][P][Q*K] bf16, boxes of {64 columns, 32 rows, 1 image}, SWIZZLE_128B (128-byte box rows)
+int make_map_y(CUtensorMap *map, void *base, uint64_t row_elems, uint64_t P, uint64_t N) {
+    encode_tiled_fn enc;
+    int rc = get_encode(&enc);
+    if (rc) return rc;
+    cuuint64_t dims[3] = {row_elems, P, N};
+    cuuint64_t strides[2] = {row_elems * 2, row_elems * 2 * P};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        pcnn_set_error("cuTensorMapEncodeTiled failed (%d) for the output tensor", (int)r);
         return PCNN_ERR_CUDA;
     }
     return PCNN_OK;
@@ -394,6 +451,7 @@ extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int 
     p.n_qtiles = (Q + Qt - 1) / Qt;
     p.act = act;
     p.y_row_elems = (long long)Q * K;
+    p.tma_store = (H % 32 == 0 && ((long long)Q * K * 2) % 16 == 0) ? 1 : 0;
     // Toeplitz operands: T_{v,r}[(ql, k)][kk] = f[k][r][s][c] where kk = delta_v + (ql + s) * C + c
     std::vector<uint16_t> t((size_t)V * R * p.ncols * TC_KCHUNK, 0);
     for (int v = 0; v < V; ++v) {
@@ -445,9 +503,14 @@ extern "C" int pcnn_conv_tc_fwd(pcnn_ctx *ctx, pcnn_conv_plan *plan, const void 
     int rc = make_map_2d(&map_x, const_cast<void *>(x_bf16), (uint64_t)plan->row_pitch, (uint64_t)p.n_img * p.H,
                          (uint64_t)plan->row_pitch * 2, TC_KCHUNK, TC_M);
     if (rc) return rc;
+    CUtensorMap map_y = map_x;                          // placeholder when the direct-store epilogue is used
+    if (p.tma_store) {
+        PCNN_REQUIRE(((uintptr_t)y_bf16 & 15) == 0, PCNN_ERR_ARG, "pcnn_conv_tc_fwd: output must be 16-byte aligned");
+        if ((rc = make_map_y(&map_y, y_bf16, (uint64_t)p.y_row_elems, (uint64_t)p.P, (uint64_t)p.n_img))) return rc;
+    }
     const int ntiles = p.n_mtiles * p.n_qtiles;
     const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
-    k_conv_tc_fwd<<<grid, TC_THREADS, conv_tc_smem_bytes(p.V, p.R, p.ncols, p.stages), ctx->stream>>>(map_x, plan->map_b, p);
+    k_conv_tc_fwd<<<grid, TC_THREADS, conv_tc_smem_bytes(p.V, p.R, p.ncols, p.stages), ctx->stream>>>(map_x, plan->map_b, map_y, p);
     PCNN_CHECK_LAUNCH(ctx);
     return PCNN_OK;
 }
