@@ -30,11 +30,12 @@
 
 namespace {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;         // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_M = 128;          // output rows per tile (TMEM lanes)
 constexpr int TC_KCHUNK = 32;      // bf16 elements per filter row r (64 B = one SWIZZLE_64B span)
 constexpr int TC_MAX_STAGES = 4;
-constexpr int TC_SMEM_BUDGET = 220 * 1024;
+constexpr int TC_SMEM_BUDGET = 225 * 1024;
 constexpr int TC_MAX_R = 5;
 constexpr int A_TILE_BYTES = TC_M * TC_KCHUNK * 2;   // 8 KB
 constexpr int OUT_STAGE_BYTES = 2 * 4096;            // per epilogue warp: two [32 rows x 64 cols] bf16 boxes for the TMA store
@@ -108,8 +109,8 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile with 64-byte rows written by TMA with CU_TENSOR_MAP_SWIZZLE_64B: canonical layout
 // Swizzle<2,4,3> o ((8,n),2):((4,SBO),1) in 16-byte units (cute/arch/mma_sm100_desc.hpp): 8-row groups 512 B apart.
@@ -142,11 +143,11 @@ struct ConvTcSmemView {
         return base + (size_t)V * R * bmat + (size_t)stages * R * A_TILE_BYTES + (size_t)epi_warp * OUT_STAGE_BYTES;
     }
     __device__ __forceinline__ ConvTcCtl &ctl() const {
-        return *reinterpret_cast<ConvTcCtl *>(base + (size_t)V * R * bmat + (size_t)stages * R * A_TILE_BYTES + 4 * OUT_STAGE_BYTES);
+        return *reinterpret_cast<ConvTcCtl *>(base + (size_t)V * R * bmat + (size_t)stages * R * A_TILE_BYTES + TC_EPI_WARPS * OUT_STAGE_BYTES);
     }
 };
 static size_t conv_tc_smem_bytes(int V, int R, int ncols, int stages) {
-    return (size_t)V * R * ncols * TC_KCHUNK * 2 + (size_t)stages * R * A_TILE_BYTES + 4 * OUT_STAGE_BYTES + sizeof(ConvTcCtl) + 1024;
+    return (size_t)V * R * ncols * TC_KCHUNK * 2 + (size_t)stages * R * A_TILE_BYTES + TC_EPI_WARPS * OUT_STAGE_BYTES + sizeof(ConvTcCtl) + 1024;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -163,7 +164,7 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NST; ++i) { bar_init(&S.full[i], 1); bar_init(&S.empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { bar_init(&S.tfull[i], 1); bar_init(&S.tempty[i], 4); }
+        for (int i = 0; i < 2; ++i) { bar_init(&S.tfull[i], 1); bar_init(&S.tempty[i], TC_EPI_WARPS); }
         bar_init(&S.bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -230,6 +231,7 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         //    tensor and are clipped by the hardware, and the warps go straight back to draining TMEM.
         //  * direct path otherwise: 16-byte stores from registers (each lane its own row).
         const int quarter = warp & 3;                           // TMEM lanes this warp may read
+        const int colhalf = (warp - 2) >> 2;                    // two warps share a lane quarter: even / odd column boxes
         unsigned char *obuf = sv.out(warp - 2);                 // 2 x 4 KB, 1024-byte aligned
         int ob = 0;
         int it = 0;
@@ -246,16 +248,20 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 const long long m0 = (long long)mt * TC_M + quarter * 32;      // first row of this warp: n * H + p
                 const int n = (int)(m0 / p.H), pr = (int)(m0 % p.H);           // H % 32 == 0: the 32 rows share n
                 const bool group_ok = n < p.n_img && pr < p.P;
-                for (int col0 = 0; col0 < p.ncols; col0 += 64) {
+                for (int col0 = colhalf * 64; col0 < p.ncols; col0 += 128) {
                     unsigned char *buf = obuf + ob * 4096;
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer `ob` is free again
                     __syncwarp();
+                    uint32_t vv[2][32];
+                    const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + col0);
+                    tc_ld_32x32(tbase, vv[0]);                                   // both halves in flight, one wait
+                    if (col0 + 32 < p.ncols) tc_ld_32x32(tbase + 32, vv[1]);
+                    tc_wait_ld();
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         const int c0 = col0 + half * 32;
                         if (c0 < p.ncols) {
-                            uint32_t v[32];
-                            tc_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+                            uint32_t (&v)[32] = vv[half];
 #pragma unroll
                             for (int j = 0; j < 32; j += 8) {
                                 float f[8];
@@ -289,9 +295,10 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 const int n = (int)(m / p.H), pr = (int)(m % p.H);
                 const bool row_ok = n < p.n_img && pr < p.P;
                 __nv_bfloat16 *yrow = p.y + ((long long)n * p.P + pr) * p.y_row_elems + (long long)q0 * p.K;
-                for (int c0 = 0; c0 < p.ncols; c0 += 32) {
+                for (int c0 = colhalf * 32; c0 < p.ncols; c0 += 64) {
                     uint32_t v[32];
                     tc_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+                    tc_wait_ld();
                     if (row_ok) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
@@ -435,7 +442,7 @@ extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int 
         int max_delta = 0;
         for (int i = 0; i < v; ++i) max_delta = max_delta > (i * t * C) % 8 ? max_delta : (i * t * C) % 8;
         if (max_delta + (t + S - 1) * C > TC_KCHUNK) continue;
-        const size_t fixed = (size_t)v * R * t * K * TC_KCHUNK * 2 + 4 * OUT_STAGE_BYTES + sizeof(ConvTcCtl) + 1024;
+        const size_t fixed = (size_t)v * R * t * K * TC_KCHUNK * 2 + TC_EPI_WARPS * OUT_STAGE_BYTES + sizeof(ConvTcCtl) + 1024;
         if (fixed + 2 * (size_t)R * A_TILE_BYTES > (size_t)TC_SMEM_BUDGET) continue;
         int st = (int)(((size_t)TC_SMEM_BUDGET - fixed) / ((size_t)R * A_TILE_BYTES));
         Qt = t; V = v; stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
