@@ -217,8 +217,10 @@ int pcnn_softmax_ce(pcnn_ctx *ctx, const float *logits, const uint8_t *labels, i
  * (LeNet c1: Qt = 24; 224x224x3 -> 64 x 3x3: Qt = 4).  PARITY UNPINNED by the reference (it has no bf16 path): the
  * checker is orc_conv_fwd_nhwc in oracle/lenet_oracle.c on the bf16-rounded operands. */
 typedef struct pcnn_conv_plan pcnn_conv_plan;
-int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int C, int K, int R, int S, int row_pitch, int act,
-                             const float *filt_host, const float *bias_host, pcnn_conv_plan **plan_out);
+int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int C, int K, int R, int S, int row_pitch,
+                             int image_rows /* rows between consecutive images in memory, >= H; 0 = H.  A multiple of
+                                               32 lets the epilogue use asynchronous TMA stores */,
+                             int act, const float *filt_host, const float *bias_host, pcnn_conv_plan **plan_out);
 int pcnn_conv_tc_plan_destroy(pcnn_ctx *ctx, pcnn_conv_plan *plan);
 int pcnn_conv_tc_fwd(pcnn_ctx *ctx, pcnn_conv_plan *plan, const void *x_bf16_dev, void *y_bf16_dev);
 /* fp32 [rows][w] -> bf16 [rows][pitch] with zero padding (builds the padded activation rows the TMA descriptor needs) */

@@ -423,12 +423,15 @@ struct pcnn_conv_plan {
 };
 
 extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int C, int K, int R, int S, int row_pitch,
-                                        int act, const float *filt_host, const float *bias_host, pcnn_conv_plan **out) {
+                                        int image_rows, int act, const float *filt_host, const float *bias_host,
+                                        pcnn_conv_plan **out) {
     PCNN_REQUIRE(ctx && filt_host && out, PCNN_ERR_ARG, "pcnn_conv_tc_plan_create: NULL argument");
     PCNN_REQUIRE(N > 0 && H >= R && W >= S && C > 0 && K > 0 && R > 0 && R <= TC_MAX_R && S > 0, PCNN_ERR_ARG,
                  "pcnn_conv_tc_plan_create: bad shape N=%d H=%d W=%d C=%d K=%d R=%d S=%d", N, H, W, C, K, R, S);
     PCNN_REQUIRE(row_pitch >= W * C && row_pitch % 8 == 0, PCNN_ERR_ARG,
                  "pcnn_conv_tc_plan_create: row pitch %d must be >= W*C and a multiple of 8 elements (TMA 16-byte strides)", row_pitch);
+    if (image_rows <= 0) image_rows = H;
+    PCNN_REQUIRE(image_rows >= H, PCNN_ERR_ARG, "pcnn_conv_tc_plan_create: image pitch of %d rows is smaller than H = %d", image_rows, H);
     const int Q = W - S + 1, P = H - R + 1;
     // pixel block Qt: the TMA box must start on a 16-byte boundary, so it starts at (q0*C) & ~7 and the Toeplitz
     // operand absorbs the remainder delta = (q0*C) % 8: delta + (Qt+S-1)*C elements must fit the 32-element K chunk.
@@ -453,12 +456,12 @@ extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int 
     pcnn_conv_plan *pl = new pcnn_conv_plan();
     pl->W = W; pl->S = S; pl->row_pitch = row_pitch;
     ConvTcParams &p = pl->p;
-    p.n_img = N; p.H = H; p.P = P; p.Q = Q; p.K = K; p.R = R; p.Qt = Qt; p.ncols = Qt * K; p.C = C; p.V = V; p.stages = stages;
-    p.n_mtiles = (int)(((long long)N * H + TC_M - 1) / TC_M);
+    p.n_img = N; p.H = image_rows; p.P = P; p.Q = Q; p.K = K; p.R = R; p.Qt = Qt; p.ncols = Qt * K; p.C = C; p.V = V; p.stages = stages;
+    p.n_mtiles = (int)(((long long)N * image_rows + TC_M - 1) / TC_M);
     p.n_qtiles = (Q + Qt - 1) / Qt;
     p.act = act;
     p.y_row_elems = (long long)Q * K;
-    p.tma_store = (H % 32 == 0 && ((long long)Q * K * 2) % 16 == 0) ? 1 : 0;
+    p.tma_store = (image_rows % 32 == 0 && ((long long)Q * K * 2) % 16 == 0) ? 1 : 0;
     // Toeplitz operands: T_{v,r}[(ql, k)][kk] = f[k][r][s][c] where kk = delta_v + (ql + s) * C + c
     std::vector<uint16_t> t((size_t)V * R * p.ncols * TC_KCHUNK, 0);
     for (int v = 0; v < V; ++v) {

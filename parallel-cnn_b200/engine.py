@@ -339,7 +339,7 @@ class Engine:
 class ConvPlan:
     """bf16 tensor-core convolution plan (pcnn_conv_tc_*): filters fp32 KRSC on the host, activations NHWC bf16."""
 
-    def __init__(self, engine, N, H, W, C, K, R, S, filt, bias=None, act=0, row_pitch=None):
+    def __init__(self, engine, N, H, W, C, K, R, S, filt, bias=None, act=0, row_pitch=None, image_rows=0):
         self.engine = engine
         self.shape = (N, H, W, C, K, R, S)
         self.row_pitch = int(row_pitch if row_pitch is not None else (W * C + 7) // 8 * 8)
@@ -348,7 +348,7 @@ class ConvPlan:
         b = None if bias is None else np.ascontiguousarray(bias, np.float32)
         plan = C_.c_void_p()
         check("pcnn_conv_tc_plan_create",
-              lib().pcnn_conv_tc_plan_create(engine.ctx, N, H, W, C, K, R, S, self.row_pitch, int(act), filt.ctypes.data,
+              lib().pcnn_conv_tc_plan_create(engine.ctx, N, H, W, C, K, R, S, self.row_pitch, int(image_rows), int(act), filt.ctypes.data,
                                              None if b is None else b.ctypes.data, C_.byref(plan)))
         self.plan = plan
         self.out_shape = (N, H - R + 1, W - S + 1, K)

@@ -24,13 +24,13 @@ rng = np.random.default_rng(1234)
 only = sys.argv[1] if len(sys.argv) > 1 else "all"
 
 
-def run(name, N, H, W, C, K, R, S, act, iters):
+def run(name, N, H, W, C, K, R, S, act, iters, image_rows=0):
     pitch = (W * C + 7) // 8 * 8
     P, Q = H - R + 1, W - S + 1
     f = rng.uniform(-0.5, 0.5, (K, R, S, C)).astype(np.float32)
     b = rng.uniform(-0.5, 0.5, K).astype(np.float32)
-    plan = pkg.ConvPlan(eng, N, H, W, C, K, R, S, f, b, act=act, row_pitch=pitch)
-    x = torch.randint(0, 0x3F80, (N * H, pitch), dtype=torch.int16, device="cuda")       # positive bf16 bit patterns < 1.0
+    plan = pkg.ConvPlan(eng, N, H, W, C, K, R, S, f, b, act=act, row_pitch=pitch, image_rows=image_rows)
+    x = torch.randint(0, 0x3F80, (N * (image_rows or H), pitch), dtype=torch.int16, device="cuda")   # positive bf16 bit patterns < 1.0
     y = torch.empty((N, P, Q, K), dtype=torch.int16, device="cuda")
     for _ in range(3):
         plan.fwd(x, y)
@@ -55,6 +55,8 @@ def run(name, N, H, W, C, K, R, S, act, iters):
 if only in ("all", "lenet"):
     for N in (1024, 8192, 65536):
         run("lenet_c1_bf16_sigmoid (config 3 shape)", N, 28, 28, 1, 6, 5, 5, 1, 20)
+    for N in (8192, 65536):
+        run("lenet_c1_bf16_sigmoid, 32-row image pitch (TMA-store epilogue)", N, 28, 28, 1, 6, 5, 5, 1, 20, image_rows=32)
 if only in ("all", "cfg5"):
     for N in (1, 8, 32, 128):
         run("224x224x3->64x3x3 bf16 (config 5)", N, 224, 224, 3, 64, 3, 3, 0, 10)

@@ -73,6 +73,30 @@ def test_lenet_c1_real_digits_with_sigmoid_epilogue(eng, pkg, golden):
     assert np.abs(got - ref).max() <= 3e-2
 
 
+def test_lenet_c1_with_32_row_image_pitch_uses_tma_stores(eng, pkg, golden):
+    # images laid out [N][32 rows][32 cols] (rows 28..31 zero): the 32-row groups of the M dimension coincide with
+    # images, so the epilogue takes the asynchronous TMA-store path; output rows p >= 24 are clipped by the tensor map
+    N = 96
+    imgs = O.u8_to_f32(golden["train_u8"][:N]).reshape(N, 28, 28)
+    p = golden["params_init"]
+    filt, bias = p[0:150].reshape(6, 5, 5, 1), p[150:156]
+    xp = np.zeros((N, 32, 32), np.uint16)
+    xp[:, :28, :28] = pkg.f32_to_bf16_bits(imgs)
+    plan = pkg.ConvPlan(eng, N, 28, 28, 1, 6, 5, 5, filt, bias, act=0, row_pitch=32, image_rows=32)
+    dy = eng.to_device(np.full((N, 24, 24, 6), 0x7FC0, np.uint16))       # NaN canary: every element must be written
+    plan.fwd(eng.to_device(xp.reshape(N * 32, 32)), dy)
+    eng.sync()
+    got = pkg.bf16_bits_to_f32(dy.to_host())
+    plan.close()
+    xb = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(imgs)).reshape(N, 28, 28, 1)
+    fb = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(filt))
+    ref = np.empty((N, 24, 24, 6), np.float32)
+    O.oracle().orc_conv_fwd_nhwc(O.fp(xb.reshape(-1)), O.fp(fb.reshape(-1)), O.fp(np.ascontiguousarray(bias)), O.fp(ref.reshape(-1)),
+                                 N, 28, 28, 1, 6, 5, 5)
+    assert np.isfinite(got).all()
+    assert np.all(np.abs(got - ref) <= 2.0 ** -8 * np.abs(ref) + 1e-3)
+
+
 @pytest.mark.parametrize("N,H,W", [(1, 224, 224), (2, 64, 40), (3, 19, 23)])
 def test_config5_shape(eng, pkg, N, H, W):
     # 3 input channels, 64 filters of 3x3: pixel blocks of 4, ragged last block (222 = 55 * 4 + 2), ragged row tiles
