@@ -223,6 +223,13 @@ int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int C, int K, i
                              int act, const float *filt_host, const float *bias_host, pcnn_conv_plan **plan_out);
 int pcnn_conv_tc_plan_destroy(pcnn_ctx *ctx, pcnn_conv_plan *plan);
 int pcnn_conv_tc_fwd(pcnn_ctx *ctx, pcnn_conv_plan *plan, const void *x_bf16_dev, void *y_bf16_dev);
+/* Backward passes of the same convolution (bf16 operands, fp32 accumulation; round-1: functional FMA-pipe kernels,
+ * deterministic): weight gradient fp32 KRSC [ref: layer.h:371-395 bp_weight_c1, without its /576] and input gradient
+ * bf16 NHWC in x's layout.  row_pitch / image_rows as for the forward plan (0 = dense). */
+int pcnn_conv_wgrad(pcnn_ctx *ctx, const void *x_bf16_dev, const void *dy_bf16_dev, float *dw_f32_dev, int N, int H, int W, int C,
+                    int K, int R, int S, int row_pitch, int image_rows);
+int pcnn_conv_dgrad(pcnn_ctx *ctx, const void *dy_bf16_dev, const float *filt_f32_dev, void *dx_bf16_dev, int N, int H, int W,
+                    int C, int K, int R, int S, int row_pitch, int image_rows);
 /* fp32 [rows][w] -> bf16 [rows][pitch] with zero padding (builds the padded activation rows the TMA descriptor needs) */
 int pcnn_f32_to_bf16_rows(pcnn_ctx *ctx, const float *src_dev, void *dst_bf16_dev, long rows, int w, int pitch);
 

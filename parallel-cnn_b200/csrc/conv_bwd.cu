@@ -1,0 +1,152 @@
+// parallel-cnn_b200/csrc/conv_bwd.cu -- weight- and input-gradient of the generic NHWC bf16 convolution.
+//
+// Round-1 status: FUNCTIONAL kernels on the fp32 FMA pipe (bf16 operands, fp32 accumulation, deterministic two-stage
+// reduction, no atomics), written to complete the forward/backward set and to pin the arithmetic against the oracle.
+// They are NOT the roofline kernels: both passes move the same 6.6 MB/image as the forward pass (config 5), i.e. they are
+// HBM-bound at 170 MFLOP per 6.6 MB, which the FMA pipe cannot sustain -- the tensor-core formulation
+// (the transposed row-Toeplitz GEMM of conv_tc.cu with MN-major operands and split-K over rows) is the round-2 item.
+//   wgrad  dw[k][r][s][c] = sum_{n,p,q} dy[n][p][q][k] * x[n][p+r][q+s][c]          [ref: layer.h:371-395 without the /576]
+//   dgrad  dx[n][h][w][c] = sum_{k,r,s} dy[n][h-r][w-s][k] * f[k][r][s][c]          (the reference never needs it: c1 is the first layer)
+#include "pcnn_internal.h"
+
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int WG_THREADS = 256;
+constexpr int WG_MAXO = 8;            // outputs per thread: K*R*S*C <= 2048
+
+struct ConvShape {
+    int N, H, W, C, K, R, S, P, Q;
+    int row_pitch;                    // elements between rows of x
+    int image_rows;                   // rows between images of x
+};
+
+__device__ __forceinline__ float bf(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+
+// one CTA walks output rows (n, p) = blockIdx.x, + gridDim.x, ...; thread t owns outputs t, t + 256, ...
+__global__ void __launch_bounds__(WG_THREADS) k_conv_wgrad_partial(const __nv_bfloat16 *__restrict__ x,
+                                                                    const __nv_bfloat16 *__restrict__ dy, float *__restrict__ slots,
+                                                                    const ConvShape s) {
+    const int nout = s.K * s.R * s.S * s.C;
+    int k[WG_MAXO], xoff[WG_MAXO];
+    float acc[WG_MAXO];
+#pragma unroll
+    for (int i = 0; i < WG_MAXO; ++i) {
+        const int o = threadIdx.x + i * WG_THREADS;
+        acc[i] = 0.0f;
+        k[i] = 0;
+        xoff[i] = -1;
+        if (o < nout) {
+            const int c = o % s.C, ss = (o / s.C) % s.S, r = (o / (s.C * s.S)) % s.R;
+            k[i] = o / (s.C * s.S * s.R);
+            xoff[i] = r * s.row_pitch + ss * s.C + c;
+        }
+    }
+    const long rows = (long)s.N * s.P;
+    for (long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int n = (int)(row / s.P), p = (int)(row % s.P);
+        const __nv_bfloat16 *xr = x + ((long)n * s.image_rows + p) * s.row_pitch;
+        const __nv_bfloat16 *dr = dy + row * s.Q * s.K;
+        for (int q = 0; q < s.Q; ++q) {
+#pragma unroll
+            for (int i = 0; i < WG_MAXO; ++i)
+                if (xoff[i] >= 0) acc[i] = fmaf(bf(dr + q * s.K + k[i]), bf(xr + q * s.C + xoff[i]), acc[i]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < WG_MAXO; ++i) {
+        const int o = threadIdx.x + i * WG_THREADS;
+        if (o < nout) slots[(long)blockIdx.x * nout + o] = acc[i];
+    }
+}
+
+__global__ void k_conv_wgrad_reduce(const float *__restrict__ slots, float *__restrict__ dw, int nslots, int nout) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nout) return;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    int k = 0;
+    for (; k + 3 < nslots; k += 4) {
+        s0 += slots[(long)k * nout + o];
+        s1 += slots[(long)(k + 1) * nout + o];
+        s2 += slots[(long)(k + 2) * nout + o];
+        s3 += slots[(long)(k + 3) * nout + o];
+    }
+    for (; k < nslots; ++k) s0 += slots[(long)k * nout + o];
+    dw[o] = (s0 + s1) + (s2 + s3);
+}
+
+// one thread per input element (n, h, w, c)
+__global__ void __launch_bounds__(256) k_conv_dgrad(const __nv_bfloat16 *__restrict__ dy, const float *__restrict__ f,
+                                                   __nv_bfloat16 *__restrict__ dx, const ConvShape s) {
+    const long total = (long)s.N * s.H * s.W * s.C;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % s.C);
+        const int w = (int)((idx / s.C) % s.W);
+        const int h = (int)((idx / ((long)s.C * s.W)) % s.H);
+        const int n = (int)(idx / ((long)s.C * s.W * s.H));
+        float acc = 0.0f;
+        for (int r = 0; r < s.R; ++r) {
+            const int p = h - r;
+            if (p < 0 || p >= s.P) continue;
+            for (int ss = 0; ss < s.S; ++ss) {
+                const int q = w - ss;
+                if (q < 0 || q >= s.Q) continue;
+                const __nv_bfloat16 *d = dy + (((long)n * s.P + p) * s.Q + q) * s.K;
+                const float *fp = f + ((long)r * s.S + ss) * s.C + c;
+                for (int k = 0; k < s.K; ++k) acc = fmaf(bf(d + k), fp[(long)k * s.R * s.S * s.C], acc);
+            }
+        }
+        dx[((long)n * s.image_rows + h) * s.row_pitch + w * s.C + c] = __float2bfloat16_rn(acc);
+    }
+}
+
+int check_shape(const char *fn, int N, int H, int W, int C, int K, int R, int S, int row_pitch, int image_rows, ConvShape *out) {
+    PCNN_REQUIRE(N > 0 && C > 0 && K > 0 && R > 0 && S > 0 && H >= R && W >= S, PCNN_ERR_ARG, "%s: bad shape", fn);
+    if (row_pitch <= 0) row_pitch = W * C;
+    if (image_rows <= 0) image_rows = H;
+    PCNN_REQUIRE(row_pitch >= W * C && image_rows >= H, PCNN_ERR_ARG, "%s: pitches smaller than the image", fn);
+    out->N = N; out->H = H; out->W = W; out->C = C; out->K = K; out->R = R; out->S = S;
+    out->P = H - R + 1; out->Q = W - S + 1; out->row_pitch = row_pitch; out->image_rows = image_rows;
+    return PCNN_OK;
+}
+
+}  // namespace
+
+extern "C" int pcnn_conv_wgrad(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16, float *dw_f32, int N, int H, int W, int C,
+                               int K, int R, int S, int row_pitch, int image_rows) {
+    PCNN_REQUIRE(ctx && x_bf16 && dy_bf16 && dw_f32, PCNN_ERR_ARG, "pcnn_conv_wgrad: NULL argument");
+    ConvShape s;
+    int rc = check_shape("pcnn_conv_wgrad", N, H, W, C, K, R, S, row_pitch, image_rows, &s);
+    if (rc) return rc;
+    const int nout = K * R * S * C;
+    PCNN_REQUIRE(nout <= WG_THREADS * WG_MAXO, PCNN_ERR_ARG, "pcnn_conv_wgrad: K*R*S*C = %d exceeds %d", nout, WG_THREADS * WG_MAXO);
+    pcnn_device_guard g(ctx->device);
+    const long rows = (long)N * s.P;
+    int grid = (int)(rows < (long)ctx->sm_count * 8 ? rows : (long)ctx->sm_count * 8);
+    float *slots = nullptr;
+    PCNN_CUDA(cudaMallocAsync((void **)&slots, (size_t)grid * nout * sizeof(float), ctx->stream));
+    k_conv_wgrad_partial<<<grid, WG_THREADS, 0, ctx->stream>>>(reinterpret_cast<const __nv_bfloat16 *>(x_bf16),
+                                                              reinterpret_cast<const __nv_bfloat16 *>(dy_bf16), slots, s);
+    PCNN_CHECK_LAUNCH(ctx);
+    k_conv_wgrad_reduce<<<(nout + 127) / 128, 128, 0, ctx->stream>>>(slots, dw_f32, grid, nout);
+    PCNN_CHECK_LAUNCH(ctx);
+    PCNN_CUDA(cudaFreeAsync(slots, ctx->stream));
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_conv_dgrad(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f32_dev, void *dx_bf16, int N, int H, int W,
+                               int C, int K, int R, int S, int row_pitch, int image_rows) {
+    PCNN_REQUIRE(ctx && dy_bf16 && filt_f32_dev && dx_bf16, PCNN_ERR_ARG, "pcnn_conv_dgrad: NULL argument");
+    ConvShape s;
+    int rc = check_shape("pcnn_conv_dgrad", N, H, W, C, K, R, S, row_pitch, image_rows, &s);
+    if (rc) return rc;
+    pcnn_device_guard g(ctx->device);
+    const long total = (long)N * H * W * C;
+    long blocks = (total + 255) / 256;
+    if (blocks > (long)ctx->sm_count * 16) blocks = (long)ctx->sm_count * 16;
+    k_conv_dgrad<<<(int)blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const __nv_bfloat16 *>(dy_bf16), filt_f32_dev,
+                                                      reinterpret_cast<__nv_bfloat16 *>(dx_bf16), s);
+    PCNN_CHECK_LAUNCH(ctx);
+    return PCNN_OK;
+}

@@ -332,6 +332,12 @@ class Engine:
     def maxpool_bwd(self, dout, argmax, din, planes, H, W, k):
         self._call("pcnn_maxpool_bwd", _p(dout), _p(argmax), _p(din), int(planes), int(H), int(W), int(k))
 
+    def conv_wgrad(self, x_bf16, dy_bf16, dw_f32, N, H, W, Cin, K, R, S, row_pitch=0, image_rows=0):
+        self._call("pcnn_conv_wgrad", _p(x_bf16), _p(dy_bf16), _p(dw_f32), N, H, W, Cin, K, R, S, int(row_pitch), int(image_rows))
+
+    def conv_dgrad(self, dy_bf16, filt_f32, dx_bf16, N, H, W, Cin, K, R, S, row_pitch=0, image_rows=0):
+        self._call("pcnn_conv_dgrad", _p(dy_bf16), _p(filt_f32), _p(dx_bf16), N, H, W, Cin, K, R, S, int(row_pitch), int(image_rows))
+
     def softmax_ce(self, logits, labels, B, n, prob=None, d=None, loss=None):
         self._call("pcnn_softmax_ce", _p(logits), _p(labels), int(B), int(n), _p(prob), _p(d), _p(loss))
 

@@ -113,3 +113,46 @@ def test_plan_rejects_unsupported_shapes(eng, pkg):
         pkg.ConvPlan(eng, 1, 32, 32, 64, 64, 3, 3, np.zeros(64 * 9 * 64, np.float32))      # (Qt+S-1)*C > 32 for every Qt
     with pytest.raises(pkg.PcnnError):
         pkg.ConvPlan(eng, 1, 28, 28, 1, 6, 5, 5, np.zeros(150, np.float32), row_pitch=28)   # pitch not a multiple of 8
+
+
+@pytest.mark.parametrize("shape", [(4, 28, 28, 1, 6, 5, 5), (2, 40, 36, 3, 64, 3, 3), (3, 17, 21, 2, 16, 3, 5)])
+def test_conv_wgrad_and_dgrad_vs_oracle(eng, pkg, shape):
+    """Backward passes of the generic convolution (csrc/conv_bwd.cu) against orc_conv_wgrad_nhwc / orc_conv_dgrad_nhwc on
+    the same bf16-rounded operands: fp32 accumulation on both sides (the oracle in double), so
+    wgrad (fp32 out) rel-L2 <= 1e-5, dgrad (bf16 out) |d| <= 2^-8 |ref| + 1e-3."""
+    N, H, W, C, K, R, S = shape
+    rng = np.random.default_rng(sum(shape))
+    P, Q = H - R + 1, W - S + 1
+    x = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(rng.uniform(0, 1, (N, H, W, C)).astype(np.float32)))
+    dy = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(rng.uniform(-1, 1, (N, P, Q, K)).astype(np.float32)))     # config 5: dy ~ U[-1,1)
+    f = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(rng.uniform(-0.5, 0.5, (K, R, S, C)).astype(np.float32)))
+    dw_ref = np.empty((K, R, S, C), np.float32)
+    dx_ref = np.empty((N, H, W, C), np.float32)
+    O.oracle().orc_conv_wgrad_nhwc(O.fp(x.reshape(-1)), O.fp(dy.reshape(-1)), O.fp(dw_ref.reshape(-1)), N, H, W, C, K, R, S)
+    O.oracle().orc_conv_dgrad_nhwc(O.fp(dy.reshape(-1)), O.fp(f.reshape(-1)), O.fp(dx_ref.reshape(-1)), N, H, W, C, K, R, S)
+    dxb, dyb = eng.to_device(pkg.f32_to_bf16_bits(x)), eng.to_device(pkg.f32_to_bf16_bits(dy))
+    dw = eng.array((K, R, S, C))
+    eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
+    got_w = dw.to_host()
+    assert np.linalg.norm((got_w - dw_ref).astype(np.float64)) / np.linalg.norm(dw_ref.astype(np.float64)) <= 1e-5
+    eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
+    assert np.array_equal(dw.to_host().view(np.uint32), got_w.view(np.uint32))                                  # deterministic
+    dxo = eng.array((N, H, W, C), np.uint16)
+    eng.conv_dgrad(dyb, eng.to_device(f), dxo, N, H, W, C, K, R, S)
+    got_x = pkg.bf16_bits_to_f32(dxo.to_host())
+    assert np.all(np.abs(got_x - dx_ref) <= 2.0 ** -8 * np.abs(dx_ref) + 1e-3)
+
+
+def test_lenet_wgrad_matches_reference_bp_weight_c1(eng, pkg, golden):
+    """bp_weight_c1 of the reference (layer.h:371-395) = this wgrad / 576 for one sample, up to bf16 rounding of the inputs."""
+    p = golden["params_init"]
+    img = O.u8_to_f32(golden["train_u8"][0])
+    a = O.forward(p, img)
+    b = O.backward(p, img, int(golden["train_labels"][0]), a)
+    dpre = b[slice(*O.BACK_OFF["c1_dpre"])].reshape(6, 24, 24).transpose(1, 2, 0)           # -> [P][Q][K]
+    dw_ref = b[slice(*O.BACK_OFF["g"])][0:150].reshape(6, 5, 5, 1)
+    dw = eng.array((6, 5, 5, 1))
+    eng.conv_wgrad(eng.to_device(pkg.f32_to_bf16_bits(img.reshape(1, 28, 28, 1))), eng.to_device(pkg.f32_to_bf16_bits(dpre)), dw,
+                   1, 28, 28, 1, 6, 5, 5)
+    got = dw.to_host() / 576.0
+    assert np.linalg.norm(got - dw_ref) / np.linalg.norm(dw_ref) <= 1e-2                                       # bf16 operands
