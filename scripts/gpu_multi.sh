@@ -6,10 +6,28 @@ N=${N:-2}
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi -L | head -8
 nvidia-smi topo -m 2>/dev/null | head -12 > $OUT/topo_$N.txt
-echo "== multi-GPU parity tests"; timeout 900 python -m pytest tests/test_persist_gpu.py -m gpu -q -k two_gpu -p no:cacheprovider 2>&1 | tail -15
+for MODE in p2p nccl; do
+  echo "== parity N=$N mode=$MODE"
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) \
+      tests/mgpu_worker.py --mode $MODE 2>&1 | grep -E "MGPU|rel-L2|Error|error" | head -5
+done
 for MODE in persistent graph; do
   echo "== bench N=$N mode=$MODE"
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700 + RANDOM % 200)) \
       bench.py --gpus $N --steps ${STEPS:-2000} --warmup 100 --mode $MODE --no-cpu-baseline > $OUT/bench_n${N}_$MODE.json 2> $OUT/bench_n${N}_$MODE.err
-  echo "rc=$?"; cat $OUT/bench_n${N}_$MODE.json | cut -c1-700; tail -3 $OUT/bench_n${N}_$MODE.err
+  echo "rc=$?"; python - <<PY
+import json
+try:
+    d=json.loads(open("$OUT/bench_n${N}_$MODE.json").read().strip().splitlines()[-1])
+    print({k:d[k] for k in ("value","n_gpus","ms_per_step")}, "e2e", d["e2e"]["value"], d["config"]["step_mode"])
+except Exception as e:
+    print("no json", e); print(open("$OUT/bench_n${N}_$MODE.err").read()[-1500:])
+PY
 done
+if [ "${B1024:-0}" = "1" ]; then
+  echo "== bench N=$N persistent, 1024 per GPU (BASELINE config 4)"
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29900 + RANDOM % 100)) \
+      bench.py --gpus $N --steps 1000 --warmup 50 --batch 1024 --no-cpu-baseline > $OUT/bench_n${N}_b1024.json 2> $OUT/bench_n${N}_b1024.err
+  python -c "
+import json; d=json.loads(open('$OUT/bench_n${N}_b1024.json').read().strip().splitlines()[-1]); print({k:d[k] for k in ('value','n_gpus','ms_per_step')}, 'e2e', d['e2e']['value'])"
+fi
