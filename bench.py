@@ -182,7 +182,22 @@ def run_ours(a):
         else:                        # persistent kernel, gradient chunks exchanged in-kernel over NVLink peer memory
             handles = [None] * world
             dist.all_gather_object(handles, eng.p2p_export())
-            eng.p2p_attach(handles, rank, world)
+            ok = 1
+            try:
+                eng.p2p_attach(handles, rank, world)
+            except pkg.PcnnError as exc:             # e.g. CUDA IPC not permitted in this container
+                ok = 0
+                if rank == 0:
+                    print(f"bench.py: peer attach failed ({exc}); falling back to graph + NCCL", file=sys.stderr)
+            flag = torch.tensor([ok], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:                # all ranks take the same path
+                if ok:
+                    eng.p2p_detach()
+                uid = [pkg.Engine.comm_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0)
+                eng.comm_init_rank(uid[0], rank, world)
+                a.mode = "graph"
     eng.set_step_mode({"auto": pkg.MODE_AUTO, "graph": pkg.MODE_GRAPH, "persistent": pkg.MODE_PERSISTENT}[a.mode])
 
     def barrier():
