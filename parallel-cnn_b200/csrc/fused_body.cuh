@@ -12,10 +12,7 @@ constexpr int RED_STRIDE = 27;          // 25 c1 taps + c1 bias sum, padded to a
 
 template <typename InT> struct FusedSmem {
     alignas(16) float params[NPACK];                 // packed parameters (9,376 B)
-    alignas(16) float imgf[2][PCNN_IMG + 4];         // fp32 image, double buffered (+4 zero floats: pixel "784")
-    alignas(16) float imgs[2][PCNN_IMG + 4];         // the same image shifted by one pixel: imgs[k] = imgf[k + 1], so
-                                                     // the odd-aligned pixel pairs of FFMA2 are aligned 16-byte loads
-    alignas(16) float2 wpad[6 * 15];                 // c1 taps as pairs (w0,w1)(w2,w3)(w4,0) per filter row
+    alignas(16) float imgf[2][PCNN_IMG];             // fp32 image, double buffered
     alignas(16) InT stage[2][PCNN_IMG];              // raw staging target of the bulk copies (u8 path only)
     alignas(16) float red[NWK * RED_STRIDE];         // epilogue scratch
     float fc_red[NWARP][PCNN_F];
@@ -93,13 +90,12 @@ struct ThreadId {
 
 // register-resident accumulators of one thread, kept across all images a CTA processes in one step
 struct Acc {
-    float2 dw2[15];      // c1 tap gradients as pairs: dw2[i * 3 + jp] = (dW[i][2jp], dW[i][2jp + 1]); [.][2].y is unused
-    float dw_s1[16], dw_f[PCNN_F];
+    float dw_c1[25], dw_s1[16], dw_f[PCNN_F];
     float bsum_c1, bsum_s1, gfb, err_acc;
     int wrong;
     __device__ __forceinline__ void zero() {
 #pragma unroll
-        for (int i = 0; i < 15; ++i) dw2[i] = make_float2(0.0f, 0.0f);
+        for (int i = 0; i < 25; ++i) dw_c1[i] = 0.0f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) dw_s1[i] = 0.0f;
 #pragma unroll
@@ -110,10 +106,6 @@ struct Acc {
 };
 
 template <typename InT> __device__ __forceinline__ void init_barriers(FusedSmem<InT> &S) {
-    if (threadIdx.x < 16) {   // zero the 4-float tails of the image buffers once (never written afterwards)
-        const int b = threadIdx.x >> 3, w = (threadIdx.x >> 2) & 1, k = threadIdx.x & 3;
-        (w ? S.imgs[b] : S.imgf[b])[PCNN_IMG + k] = 0.0f;
-    }
     if (threadIdx.x == 0) {
         mbar_init(&S.mbar[0], 1);
         mbar_init(&S.mbar[1], 1);
@@ -155,30 +147,15 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
     const unsigned parity = (li >> 1) & 1;
     // ---- P0: the image has landed; convert to fp32 (u8 path), fetch the label
     mbar_wait(&S.mbar[buf], parity);
-    if (t < 196) {   // pixels 4t .. 4t+3 (+ the next one for the shifted copy)
-        float4 f;
-        float nx;
-        if (IS_U8) {
-            const unsigned char *sp = reinterpret_cast<const unsigned char *>(S.stage[buf]);
-            const uchar4 q = reinterpret_cast<const uchar4 *>(sp)[t];
-            f = make_float4(pixel_to_float(q.x), pixel_to_float(q.y), pixel_to_float(q.z), pixel_to_float(q.w));
-            nx = t < 195 ? pixel_to_float(sp[4 * t + 4]) : 0.0f;
+    if (IS_U8) {
+        if (t < 196) {
+            uchar4 q = reinterpret_cast<const uchar4 *>(S.stage[buf])[t];
+            float4 f = make_float4(pixel_to_float(q.x), pixel_to_float(q.y), pixel_to_float(q.z), pixel_to_float(q.w));
             reinterpret_cast<float4 *>(S.imgf[buf])[t] = f;
-        } else {
-            f = reinterpret_cast<const float4 *>(S.imgf[buf])[t];
-            nx = S.imgf[buf][4 * t + 4];                       // element 784 is the zero tail
         }
-        reinterpret_cast<float4 *>(S.imgs[buf])[t] = make_float4(f.y, f.z, f.w, nx);
     }
     if (t == NWK && label_ptr) S.label[buf] = (int)*label_ptr;
-    if (params_parity >= 0) {
-        mbar_wait(&S.mbar[2], (unsigned)params_parity);
-        if (t >= 128 && t < 218) {                              // a fresh parameter block: rebuild the padded tap pairs
-            const int e = t - 128, mm = e / 15, i = (e % 15) / 3, jp = e % 3;
-            const float *w = S.params + OFF_C1W + mm * 25 + i * 5 + 2 * jp;
-            S.wpad[e] = make_float2(w[0], jp < 2 ? w[1] : 0.0f);
-        }
-    }
+    if (params_parity >= 0) mbar_wait(&S.mbar[2], (unsigned)params_parity);
     __syncthreads();                                                         // sync #1
     if (t == 0 && next_src) issue_image(S, buf ^ 1, next_src);
     // Single-lane blocks (TMA issue by lane 0 of warp 0, label fetch by lane 24 of warp 6) leave their warp diverged:
@@ -193,38 +170,29 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
 #pragma unroll
     for (int q = 0; q < PCNN_F; ++q) fcp[q] = 0.0f;
     if (id.worker) {
-        // 5x5 valid conv on the packed-fp32 pipe (FFMA2, sm_100): the two lanes of a pair are the taps (j, j+1) of one
-        // output, the operand pair (pixel c, pixel c+1) comes from the image (c even) or its shifted copy (c odd).
-        // acc2[p] = (sum over even taps, sum over odd taps); 240 FFMA2 instead of 400 FFMA per image.
-        const int poff = (4 * id.wx) * 28 + 4 * id.wy;
-        const float *ip = S.imgf[buf] + poff, *ips = S.imgs[buf] + poff;
-        float2 acc2[16];
-#pragma unroll
-        for (int p = 0; p < 16; ++p) acc2[p] = make_float2(0.0f, 0.0f);
-        const float2 *w2p = S.wpad + id.m * 15;
+        const float *ip = S.imgf[buf] + (4 * id.wx) * 28 + 4 * id.wy;
+        float in[8][8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const float4 e0 = *reinterpret_cast<const float4 *>(ip + r * 28), e1 = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
-            const float4 o0 = *reinterpret_cast<const float4 *>(ips + r * 28), o1 = *reinterpret_cast<const float4 *>(ips + r * 28 + 4);
-            float2 P[8];                                   // P[c] = (pixel c, pixel c + 1) of patch row r
-            P[0] = make_float2(e0.x, e0.y); P[2] = make_float2(e0.z, e0.w); P[4] = make_float2(e1.x, e1.y); P[6] = make_float2(e1.z, e1.w);
-            P[1] = make_float2(o0.x, o0.y); P[3] = make_float2(o0.z, o0.w); P[5] = make_float2(o1.x, o1.y); P[7] = make_float2(o1.z, o1.w);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int ox = r - i;
-                if (ox >= 0 && ox < 4) {
-#pragma unroll
-                    for (int jp = 0; jp < 3; ++jp) {
-                        const float2 w2 = w2p[i * 3 + jp];
-#pragma unroll
-                        for (int oy = 0; oy < 4; ++oy) acc2[ox * 4 + oy] = __ffma2_rn(P[oy + 2 * jp], w2, acc2[ox * 4 + oy]);
-                    }
-                }
-            }
+            float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
+            float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
+            in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = lo.z; in[r][3] = lo.w;
+            in[r][4] = hi.x; in[r][5] = hi.y; in[r][6] = hi.z; in[r][7] = hi.w;
         }
         float acc[16];
 #pragma unroll
-        for (int p = 0; p < 16; ++p) acc[p] = acc2[p].x + acc2[p].y;
+        for (int p = 0; p < 16; ++p) acc[p] = 0.0f;
+        const float *wc = S.params + OFF_C1W + id.m * 25;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const float w = wc[i * 5 + j];
+#pragma unroll
+                for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                    for (int oy = 0; oy < 4; ++oy) acc[ox * 4 + oy] = fmaf(in[ox + i][oy + j], w, acc[ox * 4 + oy]);
+            }
         const float bc = S.params[OFF_C1B + id.m];
         float s1pre = 0.0f;
 #pragma unroll
@@ -307,34 +275,27 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
             bs += dpc[p];
         }
         A.bsum_c1 += bs;                                                                    // bp_bias_c1 accumulator, layer.h:400-410
-        // bp_weight_c1, layer.h:371-395 (the /576 is applied once in the epilogue), again on FFMA2: the pair lanes are
-        // the taps (j, j+1) = (2jp, 2jp+1), operands (pixel c, pixel c+1) x (d, d)
-        const int poff = (4 * id.wx) * 28 + 4 * id.wy;
-        const float *ip = S.imgf[buf] + poff, *ips = S.imgs[buf] + poff;
-        float2 dd[16];
-#pragma unroll
-        for (int p = 0; p < 16; ++p) dd[p] = make_float2(dpc[p], dpc[p]);
+        // bp_weight_c1, layer.h:371-395 (the /576 is applied once in the epilogue)
+        const float *ip = S.imgf[buf] + (4 * id.wx) * 28 + 4 * id.wy;
+        float in[8][8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            const float4 e0 = *reinterpret_cast<const float4 *>(ip + r * 28), e1 = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
-            const float4 o0 = *reinterpret_cast<const float4 *>(ips + r * 28), o1 = *reinterpret_cast<const float4 *>(ips + r * 28 + 4);
-            float2 P[8];
-            P[0] = make_float2(e0.x, e0.y); P[2] = make_float2(e0.z, e0.w); P[4] = make_float2(e1.x, e1.y); P[6] = make_float2(e1.z, e1.w);
-            P[1] = make_float2(o0.x, o0.y); P[3] = make_float2(o0.z, o0.w); P[5] = make_float2(o1.x, o1.y); P[7] = make_float2(o1.z, o1.w);
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-                const int ox = r - i;
-                if (ox >= 0 && ox < 4) {
-#pragma unroll
-                    for (int jp = 0; jp < 3; ++jp) {
-                        float2 s = A.dw2[i * 3 + jp];
-#pragma unroll
-                        for (int oy = 0; oy < 4; ++oy) s = __ffma2_rn(P[oy + 2 * jp], dd[ox * 4 + oy], s);
-                        A.dw2[i * 3 + jp] = s;
-                    }
-                }
-            }
+            float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
+            float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
+            in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = lo.z; in[r][3] = lo.w;
+            in[r][4] = hi.x; in[r][5] = hi.y; in[r][6] = hi.z; in[r][7] = hi.w;
         }
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                float s = A.dw_c1[i * 5 + j];
+#pragma unroll
+                for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                    for (int oy = 0; oy < 4; ++oy) s = fmaf(dpc[ox * 4 + oy], in[ox + i][oy + j], s);
+                A.dw_c1[i * 5 + j] = s;
+            }
     }
 }
 
@@ -346,10 +307,7 @@ __device__ __forceinline__ void cta_epilogue(FusedSmem<InT> &S, const ThreadId &
     __syncthreads();
     if (id.worker) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i)
-#pragma unroll
-            for (int j = 0; j < 5; ++j)
-                S.red[t * RED_STRIDE + i * 5 + j] = (j & 1) ? A.dw2[i * 3 + (j >> 1)].y : A.dw2[i * 3 + (j >> 1)].x;
+        for (int i = 0; i < 25; ++i) S.red[t * RED_STRIDE + i] = A.dw_c1[i];
         S.red[t * RED_STRIDE + 25] = A.bsum_c1;
 #pragma unroll
         for (int q = 0; q < PCNN_F; ++q) slot[OFF_FW + q * PCNN_S1 + t] = A.dw_f[q];   // column t is private to this worker
