@@ -100,7 +100,6 @@ struct pcnn_ctx {
     int persist_cap = 0;                    // co-resident CTAs of k_train_persist on this device
     bool persist_used = false;
     unsigned *d_bar = nullptr;              // grid barrier counter
-    uint2 *d_params_ll = nullptr;           // [NPACK] {value, step id} words: parameter broadcast of the persistent kernel
     int *d_abort = nullptr;                 // set by a spin loop that ran out of budget
     long long *d_trace = nullptr;           // optional phase timestamps of the persistent kernel (pcnn_persist_trace)
     unsigned p2p_step_id = 0;               // steps issued so far (flag values of the peer exchange)

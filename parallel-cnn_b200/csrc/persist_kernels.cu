@@ -39,7 +39,6 @@ struct PersistArgs {
     int B, nsteps, rank, world, rank_local;
     float dt;
     // peer exchange (world > 1)
-    uint2 *params_ll;         // [NPACK] words {updated value bits, step id}: the intra-GPU parameter broadcast
     uint2 *inbox;             // local  [2][world][NPACK] words {value bits, step id}
     uint2 *peer_inbox[PCNN_MAX_PEERS];
     unsigned step_base;       // id of the step before the first one of this launch (ids are unique per context lifetime)
@@ -130,6 +129,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
 
     init_barriers(S);
     int li = 0;                 // CTA-local running image counter (staging buffer + mbarrier phase)
+    unsigned pphase = 0;        // uses of the parameter barrier
     unsigned nbar = 0;          // grid barriers passed
     if (t == 0) {
         issue_params(S, a.params);
@@ -149,10 +149,11 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         for (int b = c; b < nb; b += G, ++li) {
             const int bn = b + G;
             image_pass<InT, true>(S, id, li, lab_base + b, bn < nb ? img_base + (long long)bn * PCNN_IMG : nullptr,
-                                  (first && s == 0) ? 0 : -1, A, ev);     // only step 0 loads its parameters by TMA
+                                  first ? (int)(pphase & 1) : -1, A, ev);
             first = false;
         }
-        if (first && s == 0) mbar_wait(&S.mbar[2], 0);  // never leave the parameter copy of step 0 unconsumed
+        if (first) mbar_wait(&S.mbar[2], pphase & 1);   // image-less CTAs still consume this parameter phase
+        ++pphase;
         PCNN_TRACE(1);
         cta_epilogue(S, id, A, a.slots + (long long)c * NPACK);
         PCNN_TRACE(2);
@@ -178,15 +179,12 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         const int par = (int)(stepid & 1u);
         auto finalize = [&](int p, float g, float w_old) {
             a.grads[p] = g;
-            float w_new = 0.0f;
             if (p < NPARAM) {
-                w_new = updated_entry(w_old, p, g, step);
-                a.params[p] = w_new;
+                a.params[p] = updated_entry(w_old, p, g, step);
             } else {
                 *a.err_total += (double)g;
                 a.step_err[(step_idx0 + s) & (STEP_ERR_CAP - 1)] = g;
             }
-            st_ll(a.params_ll + p, w_new, stepid);                             // broadcast word for step 3 below
         };
         // Peer exchange, "low-latency" style: every 8-byte inbox word carries {value, step id}.  An 8-byte store is
         // single-copy atomic, so the receiver needs no flag round trip and the sender no system-scope fence: it polls
@@ -266,35 +264,17 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
             }
             __syncwarp();
         }
+        asm volatile("fence.proxy.async.global;" ::: "memory");               // parameter stores -> later bulk-copy reads
         PCNN_TRACE(4);
 
-        // ---- 3. next step's parameters WITHOUT a second grid barrier: every updated entry was also published as a
-        // {value, step id} word; each CTA polls the 2,344 words (all loads of a thread in flight together) straight into
-        // its shared-memory parameter block.  An owner cannot overwrite a word before every CTA has consumed it: the next
-        // write happens after the next step's barrier 1, which every CTA reaches only after this load.
-        if (more) {
-            uint2 w[MAXE];
-#pragma unroll
-            for (int i = 0; i < MAXE; ++i) {
-                const int idx = t + i * NT;
-                w[i] = idx < NPACK ? ld_ll(a.params_ll + idx) : make_uint2(0u, stepid);
-            }
-            const long long t0 = clock64();
-            for (;;) {
-                bool ok = true;
-#pragma unroll
-                for (int i = 0; i < MAXE; ++i)
-                    if (w[i].y != stepid) { ok = false; w[i] = ld_ll(a.params_ll + t + i * NT); }
-                if (ok) break;
-                if (*(volatile int *)a.abort_flag) break;
-                if (clock64() - t0 > SPIN_BUDGET) { *(volatile int *)a.abort_flag = 3; break; }
-            }
-#pragma unroll
-            for (int i = 0; i < MAXE; ++i)
-                if (t + i * NT < NPACK) S.params[t + i * NT] = __uint_as_float(w[i].x);
-            __syncthreads();
-        }
+        nbar += 1;
+        grid_barrier(a.bar, nbar * (unsigned)G, a.abort_flag);                 // parameters updated everywhere
         PCNN_TRACE(5);
+        if (t == 0 && more) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            issue_params(S, a.params);
+        }
+        __syncwarp();
         cursor = ncur;
         base = nbase;
         nb = nnb;
@@ -354,7 +334,6 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
         a.world = ctx->world;
         a.rank_local = s.rank_local ? 1 : 0;
         a.dt = ctx->lr;
-        a.params_ll = ctx->d_params_ll;
         a.inbox = ctx->p2p_inbox;
         for (int q = 0; q < PCNN_MAX_PEERS; ++q) {
             a.peer_inbox[q] = ctx->p2p_peer_inbox[q];
@@ -386,7 +365,7 @@ int pcnn_persist_check(pcnn_ctx *ctx) {
     if (flag) {
         cudaMemset(ctx->d_abort, 0, sizeof(int));
         pcnn_set_error("persistent training kernel aborted: %s wait exceeded its cycle budget",
-                       flag == 2 ? "peer-GPU exchange" : (flag == 3 ? "parameter broadcast" : "grid barrier"));
+                       flag == 2 ? "peer-GPU exchange" : "grid barrier");
         return PCNN_ERR_STATE;
     }
     return PCNN_OK;
