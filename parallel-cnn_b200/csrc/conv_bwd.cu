@@ -1,20 +1,34 @@
 // parallel-cnn_b200/csrc/conv_bwd.cu -- weight- and input-gradient of the generic NHWC bf16 convolution.
 //
-// Round-1 status: FUNCTIONAL kernels on the fp32 FMA pipe (bf16 operands, fp32 accumulation, deterministic two-stage
-// reduction, no atomics), written to complete the forward/backward set and to pin the arithmetic against the oracle.
-// They are NOT the roofline kernels: both passes move the same 6.6 MB/image as the forward pass (config 5), i.e. they are
-// HBM-bound at 170 MFLOP per 6.6 MB, which the FMA pipe cannot sustain -- the tensor-core formulation
-// (the transposed row-Toeplitz GEMM of conv_tc.cu with MN-major operands and split-K over rows) is the round-2 item.
+// Entry points + the general-shape kernels on the fp32 FMA pipe (bf16 operands, fp32 accumulation, deterministic two-stage
+// reduction, no atomics).  Shapes the tensor cores can take (64 filters; see conv_bwd_tc.cu) are routed to the tcgen05
+// kernels, which are the roofline path: both passes move the same 6.6 MB/image as the forward pass (config 5) and are
+// HBM-bound at 170 MFLOP per 6.6 MB, which the FMA pipe cannot sustain.  PCNN_CONV_BWD=fma forces the
+// FMA-pipe kernels (used by the tests to check both paths against the oracle).
 //   wgrad  dw[k][r][s][c] = sum_{n,p,q} dy[n][p][q][k] * x[n][p+r][q+s][c]          [ref: layer.h:371-395 without the /576]
 //   dgrad  dx[n][h][w][c] = sum_{k,r,s} dy[n][h-r][w-s][k] * f[k][r][s][c]          (the reference never needs it: c1 is the first layer)
 #include "pcnn_internal.h"
 
 #include <cuda_bf16.h>
+#include <stdlib.h>
+
+// conv_bwd_tc.cu
+bool pcnn_conv_dgrad_tc_ok(int N, int H, int W, int C, int K, int R, int S, const void *dy);
+bool pcnn_conv_wgrad_tc_ok(int N, int H, int W, int C, int K, int R, int S, int row_pitch, const void *x, const void *dy);
+int pcnn_conv_dgrad_tc(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f32_dev, void *dx_bf16, int N, int H, int W, int C,
+                       int K, int R, int S, int row_pitch, int image_rows);
+int pcnn_conv_wgrad_tc(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16, float *dw_f32, int N, int H, int W, int C, int K,
+                       int R, int S, int row_pitch, int image_rows);
 
 namespace {
 
+bool force_fma() {
+    const char *v = getenv("PCNN_CONV_BWD");
+    return v && v[0] == 'f';
+}
+
 constexpr int WG_THREADS = 256;
-constexpr int WG_MAXO = 8;            // outputs per thread: K*R*S*C <= 2048
+constexpr int WG_MAXO = 12;           // outputs per thread: K*R*S*C <= 3072
 
 struct ConvShape {
     int N, H, W, C, K, R, S, P, Q;
@@ -119,6 +133,8 @@ extern "C" int pcnn_conv_wgrad(pcnn_ctx *ctx, const void *x_bf16, const void *dy
     ConvShape s;
     int rc = check_shape("pcnn_conv_wgrad", N, H, W, C, K, R, S, row_pitch, image_rows, &s);
     if (rc) return rc;
+    if (!force_fma() && pcnn_conv_wgrad_tc_ok(N, H, W, C, K, R, S, s.row_pitch, x_bf16, dy_bf16))
+        return pcnn_conv_wgrad_tc(ctx, x_bf16, dy_bf16, dw_f32, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
     const int nout = K * R * S * C;
     PCNN_REQUIRE(nout <= WG_THREADS * WG_MAXO, PCNN_ERR_ARG, "pcnn_conv_wgrad: K*R*S*C = %d exceeds %d", nout, WG_THREADS * WG_MAXO);
     pcnn_device_guard g(ctx->device);
@@ -141,6 +157,8 @@ extern "C" int pcnn_conv_dgrad(pcnn_ctx *ctx, const void *dy_bf16, const float *
     ConvShape s;
     int rc = check_shape("pcnn_conv_dgrad", N, H, W, C, K, R, S, row_pitch, image_rows, &s);
     if (rc) return rc;
+    if (!force_fma() && pcnn_conv_dgrad_tc_ok(N, H, W, C, K, R, S, dy_bf16))
+        return pcnn_conv_dgrad_tc(ctx, dy_bf16, filt_f32_dev, dx_bf16, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
     pcnn_device_guard g(ctx->device);
     const long total = (long)N * H * W * C;
     long blocks = (total + 255) / 256;

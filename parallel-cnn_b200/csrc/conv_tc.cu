@@ -22,11 +22,11 @@
 //
 // Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
 // warps 2-5 = epilogue (TMEM lane quarter = warp % 4).
-#include "pcnn_internal.h"
+#include "tc_common.cuh"
 
-#include <cuda.h>
-#include <cuda_bf16.h>
 #include <vector>
+
+using namespace pcnn_tc;
 
 namespace {
 
@@ -54,77 +54,6 @@ struct ConvTcParams {
     __nv_bfloat16 *y;
     const float *bias;             // [K] or null
 };
-
-// ---- PTX wrappers ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void bar_init(unsigned long long *b, unsigned n) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(b)), "r"(n));
-}
-__device__ __forceinline__ void bar_expect_tx(unsigned long long *b, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(b)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bar_arrive(unsigned long long *b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(b)) : "memory");
-}
-__device__ __forceinline__ void bar_wait(unsigned long long *b, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "TC_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra TC_DONE;\n"
-        "bra TC_WAIT;\n"
-        "TC_DONE:\n"
-        "}\n" ::"r"(s_u32(b)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, unsigned long long *bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                     s_u32(dst)),
-                 "l"(map), "r"(c0), "r"(c1), "r"(s_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(unsigned long long *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives row (lane base + i)
-__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major operand tile with 64-byte rows written by TMA with CU_TENSOR_MAP_SWIZZLE_64B: canonical layout
-// Swizzle<2,4,3> o ((8,n),2):((4,SBO),1) in 16-byte units (cute/arch/mma_sm100_desc.hpp): 8-row groups 512 B apart.
-__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4)        // start address, bits [0,14)
-           | (1ull << 16)                                  // leading byte offset (unused for swizzled K-major)
-           | ((uint64_t)(512 >> 4) << 32)                  // stride byte offset: 8 rows * 64 B
-           | (1ull << 46)                                  // descriptor version (Blackwell)
-           | (4ull << 61);                                 // layout type SWIZZLE_64B
-}
-// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-__device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
 
 // dynamic shared memory, 1024-byte aligned:  [V*R Toeplitz matrices of ncols*64 B] [stages*R activation tiles of 8 KB] [ctl]
 struct ConvTcCtl {
@@ -348,26 +277,6 @@ __global__ void k_f32_to_bf16_rows(const float *__restrict__ src, __nv_bfloat16 
     }
 }
 
-typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int get_encode(encode_tiled_fn *out) {
-    static encode_tiled_fn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
-        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
-            pcnn_set_error("cuTensorMapEncodeTiled not available from the driver (%d)", (int)e);
-            return PCNN_ERR_CUDA;
-        }
-        fn = (encode_tiled_fn)p;
-    }
-    *out = fn;
-    return PCNN_OK;
-}
-
 int make_map_2d(CUtensorMap *map, void *base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_inner, uint32_t box_outer) {
     encode_tiled_fn enc;
     int rc = get_encode(&enc);
@@ -402,14 +311,6 @@ int make_map_y(CUtensorMap *map, void *base, uint64_t row_elems, uint64_t P, uin
         return PCNN_ERR_CUDA;
     }
     return PCNN_OK;
-}
-
-uint16_t f32_to_bf16_bits(float f) {   // round to nearest even, as __float2bfloat16_rn
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
-    u += 0x7fffu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
 }
 
 }  // namespace

@@ -52,6 +52,38 @@ def run(name, N, H, W, C, K, R, S, act, iters, image_rows=0):
     del x, y
 
 
+def run_bwd(name, N, H, W, C, K, R, S, iters):
+    """wgrad and dgrad of the same layer: algorithmic bytes = dy read + x read (wgrad) / dy read + dx written (dgrad), bf16."""
+    P, Q = H - R + 1, W - S + 1
+    xb = torch.randint(0, 0x3F80, (N, H, W, C), dtype=torch.int16, device="cuda")
+    dyb = torch.randint(0, 0x3F80, (N, P, Q, K), dtype=torch.int16, device="cuda")
+    dyb ^= (torch.randint(0, 2, (N, P, Q, K), dtype=torch.int16, device="cuda") << 15)      # random signs
+    f = torch.rand((K, R, S, C), dtype=torch.float32, device="cuda") - 0.5
+    dw = torch.empty((K, R, S, C), dtype=torch.float32, device="cuda")
+    dx = torch.empty((N, H, W, C), dtype=torch.int16, device="cuda")
+    alg = N * (H * W * C + P * Q * K) * 2
+    flops = 2.0 * N * P * Q * K * R * S * C
+    for what, fn in (("wgrad", lambda: eng.conv_wgrad(xb, dyb, dw, N, H, W, C, K, R, S)),
+                     ("dgrad", lambda: eng.conv_dgrad(dyb, f, dx, N, H, W, C, K, R, S))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        print(json.dumps({"case": name + " " + what, "N": N, "ms": ms, "img_per_s": N / (ms * 1e-3), "alg_GBps": alg / (ms * 1e-3) / 1e9,
+                          "hbm_frac": alg / (ms * 1e-3) / 1e9 / HBM, "useful_TFLOPs": flops / (ms * 1e-3) / 1e12,
+                          "path": os.environ.get("PCNN_CONV_BWD", "tc"), "working_set_MB": alg / 1e6}), flush=True)
+    del xb, dyb, dx
+
+
+if only in ("all", "bwd"):
+    for N in (8, 32, 128):
+        run_bwd("224x224x3->64x3x3 bf16 (config 5)", N, 224, 224, 3, 64, 3, 3, 10)
 if only in ("all", "lenet"):
     for N in (1024, 8192, 65536):
         run("lenet_c1_bf16_sigmoid (config 3 shape)", N, 28, 28, 1, 6, 5, 5, 1, 20)

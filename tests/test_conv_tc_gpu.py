@@ -156,3 +156,69 @@ def test_lenet_wgrad_matches_reference_bp_weight_c1(eng, pkg, golden):
                    1, 28, 28, 1, 6, 5, 5)
     got = dw.to_host() / 576.0
     assert np.linalg.norm(got - dw_ref) / np.linalg.norm(dw_ref) <= 1e-2                                       # bf16 operands
+
+
+BWD_TC_SHAPES = [(1, 224, 224, 3, 64, 3, 3),      # config 5
+                 (2, 40, 40, 3, 64, 3, 3),        # ragged row block (40 = 30 + 10), two pixel blocks
+                 (3, 37, 64, 3, 64, 3, 3),        # three pixel blocks of 28, 28, 8
+                 (2, 30, 40, 1, 64, 3, 3),        # C = 1 (85 pixels per accumulator)
+                 (1, 33, 32, 1, 64, 5, 5),        # 5x5 taps: lane quarters overlap by 4 rows
+                 (1, 19, 24, 4, 64, 3, 3)]        # C = 4
+
+
+@pytest.mark.parametrize("shape", BWD_TC_SHAPES)
+def test_tensor_core_wgrad_and_dgrad_vs_oracle_and_fma_path(eng, pkg, shape, monkeypatch):
+    """The tcgen05 backward kernels (csrc/conv_bwd_tc.cu; 64 filters) against the oracle on the same bf16-rounded operands, and
+    against the FMA-pipe kernels of csrc/conv_bwd.cu (PCNN_CONV_BWD=fma).  fp32 accumulation everywhere:
+    wgrad rel-L2 <= 1e-5 vs the oracle; dgrad |d| <= 2^-8 |ref| + 1e-3 (one bf16 rounding of the result)."""
+    N, H, W, C, K, R, S = shape
+    rng = np.random.default_rng(sum(shape) + 1)
+    P, Q = H - R + 1, W - S + 1
+    x = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(rng.uniform(0, 1, (N, H, W, C)).astype(np.float32)))
+    dy = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(rng.uniform(-1, 1, (N, P, Q, K)).astype(np.float32)))
+    f = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(rng.uniform(-0.5, 0.5, (K, R, S, C)).astype(np.float32)))
+    dw_ref = np.empty((K, R, S, C), np.float32)
+    dx_ref = np.empty((N, H, W, C), np.float32)
+    O.oracle().orc_conv_wgrad_nhwc(O.fp(x.reshape(-1)), O.fp(dy.reshape(-1)), O.fp(dw_ref.reshape(-1)), N, H, W, C, K, R, S)
+    O.oracle().orc_conv_dgrad_nhwc(O.fp(dy.reshape(-1)), O.fp(f.reshape(-1)), O.fp(dx_ref.reshape(-1)), N, H, W, C, K, R, S)
+    dxb, dyb, fd = eng.to_device(pkg.f32_to_bf16_bits(x)), eng.to_device(pkg.f32_to_bf16_bits(dy)), eng.to_device(f)
+    res = {}
+    for path in ("tc", "fma"):
+        if path == "fma":
+            monkeypatch.setenv("PCNN_CONV_BWD", "fma")
+        else:
+            monkeypatch.delenv("PCNN_CONV_BWD", raising=False)
+        launches0 = eng.launch_count()
+        dw = eng.array((K, R, S, C))
+        eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
+        got_w = dw.to_host()
+        assert np.linalg.norm((got_w - dw_ref).astype(np.float64)) / np.linalg.norm(dw_ref.astype(np.float64)) <= 1e-5, path
+        eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
+        assert np.array_equal(dw.to_host().view(np.uint32), got_w.view(np.uint32)), path                       # deterministic
+        dxo = eng.array((N, H, W, C), np.uint16)
+        eng.conv_dgrad(dyb, fd, dxo, N, H, W, C, K, R, S)
+        got_x = pkg.bf16_bits_to_f32(dxo.to_host())
+        assert np.all(np.abs(got_x - dx_ref) <= 2.0 ** -8 * np.abs(dx_ref) + 1e-3), path
+        res[path] = (got_w, got_x, eng.launch_count() - launches0)
+    # the two paths are different kernels (the dgrad launch counts differ: the tensor-core path also builds its filter variants)
+    assert res["tc"][2] != res["fma"][2]
+    assert np.linalg.norm(res["tc"][0] - res["fma"][0]) / np.linalg.norm(res["fma"][0]) <= 1e-5
+
+
+def test_tensor_core_dgrad_honours_row_and_image_pitch(eng, pkg):
+    """dx written into a padded layout (row pitch 128 elements, 48 rows per image): pad elements keep their previous contents."""
+    N, H, W, C, K, R, S = 2, 40, 40, 3, 64, 3, 3
+    rng = np.random.default_rng(5)
+    P, Q = H - R + 1, W - S + 1
+    dy = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(rng.uniform(-1, 1, (N, P, Q, K)).astype(np.float32)))
+    f = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(rng.uniform(-0.5, 0.5, (K, R, S, C)).astype(np.float32)))
+    dx_ref = np.empty((N, H, W, C), np.float32)
+    O.oracle().orc_conv_dgrad_nhwc(O.fp(dy.reshape(-1)), O.fp(f.reshape(-1)), O.fp(dx_ref.reshape(-1)), N, H, W, C, K, R, S)
+    pitch, rows = 128, 48
+    canvas = np.full((N, rows, pitch), 0x4242, np.uint16)
+    dxo = eng.to_device(canvas)
+    eng.conv_dgrad(eng.to_device(pkg.f32_to_bf16_bits(dy)), eng.to_device(f), dxo, N, H, W, C, K, R, S, row_pitch=pitch, image_rows=rows)
+    out = dxo.to_host().reshape(N, rows, pitch)
+    got = pkg.bf16_bits_to_f32(out[:, :H, :W * C].reshape(N, H, W, C))
+    assert np.all(np.abs(got - dx_ref) <= 2.0 ** -8 * np.abs(dx_ref) + 1e-3)
+    assert np.all(out[:, H:, :] == 0x4242) and np.all(out[:, :, W * C:] == 0x4242)
