@@ -175,6 +175,15 @@ int pcnn_step_errs(pcnn_ctx *ctx, float *host_out, long cap, long *count_out);
  * sustained fp32 FMA rate of this GPU under its current clocks (dependent-chain-free FFMA micro-benchmark). */
 int pcnn_time_fused_kernel(pcnn_ctx *ctx, int B, int iters, float *avg_ms_out);
 int pcnn_measure_fp32_peak(pcnn_ctx *ctx, float *tflops_out);
+/* streaming-read rate (GB/s) of a TMA load pipeline with no consumer work over a bf16 tensor [N][P][Q][64] in HBM:
+ * mode 0 = 1-D bulk copies of 16 KB, 1 = 2-D boxes of 128 pixels, 2 = the input-gradient kernel's pattern (boxes of
+ * 1 pixel x 32 rows), 3 = the weight-gradient kernel's pattern (one row of pixels per box).  The ceiling the convolution
+ * backward kernels are measured against next to the HBM copy peak. */
+int pcnn_measure_tma_read(pcnn_ctx *ctx, const void *dev_bf16, int N, int P, int Q, int mode, int iters, float *gbps_out);
+/* SM clocks per tcgen05.mma (kind::f16 bf16, K = 16, shape M x N, operands K- or MN-major in shared memory) when one thread
+ * issues `reps` of them back to back over `nacc` rotating accumulators: the issue-rate table the convolution kernels are
+ * designed against (small-N instructions are far from the tensor-pipe peak). */
+int pcnn_measure_mma_rate(pcnn_ctx *ctx, int M, int N, int a_mn_major, int b_mn_major, int nacc, int reps, float *clk_per_mma);
 
 /* ------------------------------------------------------------------ data parallelism (not in the reference)
  * Sample-sharded replicas, one process per GPU.  After pcnn_comm_init_rank every train step all-reduces the

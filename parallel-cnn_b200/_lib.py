@@ -89,6 +89,8 @@ _SIG = {
     "pcnn_step_errs": [_vp, _vp, _l, C.POINTER(_l)],
     "pcnn_time_fused_kernel": [_vp, _i, _i, C.POINTER(_f)],
     "pcnn_measure_fp32_peak": [_vp, C.POINTER(_f)],
+    "pcnn_measure_tma_read": [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_f)],
+    "pcnn_measure_mma_rate": [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(_f)],
     "pcnn_comm_unique_id": [_vp, C.POINTER(_sz)],
     "pcnn_comm_init_rank": [_vp, _vp, _i, _i],
     "pcnn_comm_destroy": [_vp],

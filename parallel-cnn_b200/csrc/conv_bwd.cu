@@ -141,13 +141,12 @@ extern "C" int pcnn_conv_wgrad(pcnn_ctx *ctx, const void *x_bf16, const void *dy
     const long rows = (long)N * s.P;
     int grid = (int)(rows < (long)ctx->sm_count * 8 ? rows : (long)ctx->sm_count * 8);
     float *slots = nullptr;
-    PCNN_CUDA(cudaMallocAsync((void **)&slots, (size_t)grid * nout * sizeof(float), ctx->stream));
+    if ((rc = pcnn_scratch(ctx, (size_t)grid * nout * sizeof(float), (void **)&slots))) return rc;
     k_conv_wgrad_partial<<<grid, WG_THREADS, 0, ctx->stream>>>(reinterpret_cast<const __nv_bfloat16 *>(x_bf16),
                                                               reinterpret_cast<const __nv_bfloat16 *>(dy_bf16), slots, s);
     PCNN_CHECK_LAUNCH(ctx);
     k_conv_wgrad_reduce<<<(nout + 127) / 128, 128, 0, ctx->stream>>>(slots, dw_f32, grid, nout);
     PCNN_CHECK_LAUNCH(ctx);
-    PCNN_CUDA(cudaFreeAsync(slots, ctx->stream));
     return PCNN_OK;
 }
 

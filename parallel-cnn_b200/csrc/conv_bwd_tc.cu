@@ -242,15 +242,19 @@ k_conv_tc_dgrad(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 // =====================================================================================================================
 //                                                       wgrad
 // =====================================================================================================================
-constexpr int WT_THREADS = 192;            // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 Hankel builders + final read-out
+constexpr int WT_BUILD_WARPS = 8;
+constexpr int WT_THREADS = 64 + 32 * WT_BUILD_WARPS;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 Hankel builders (2-5 also read out)
 constexpr int WT_MAX_STAGES = 6;
-constexpr int WT_ITEMS = 8;                // 16-byte units of the Hankel tile per builder thread
+constexpr int WT_NACC = 4;                 // independent TMEM accumulators the MMAs rotate over
+constexpr int WT_ITEMS = 4;                // 16-byte units of the Hankel tile per builder thread
 constexpr int WT_SMEM_BUDGET = 220 * 1024;
 
 struct WgradTcParams {
-    int n_img, P, Q, W, C, R, SC, nreal, nwin, Qpad, KO, stages, tmem_cols;
+    int n_img, P, Q, W, C, R, SC, nreal, nwin, Qpad, KO, stages, tmem_cols, acc_cols, nacc;
     long long x_pitch, x_image_rows;
     int xrow_bytes, xrow_stride;           // bytes copied per x row / bytes between row buffers in shared memory
+    int guard;                             // 1: the copied row carries pad elements past W*C that must read as zero
+    int dbg;                               // timing experiments only (PCNN_WGRAD_DBG): 1 = skip the Hankel build, 2 = skip the MMAs
     const __nv_bfloat16 *x;
     float *slots;                          // [grid][128 TMEM lanes][nwin]
 };
@@ -260,8 +264,11 @@ struct WgradCtl {
     uint32_t tmem_base;
 };
 
+// CT = compile-time input-channel count (the gather stride of the Hankel builder), 0 = run-time
+template <int CT>
 __global__ void __launch_bounds__(WT_THREADS, 1)
 k_conv_tc_wgrad(const __grid_constant__ CUtensorMap map_dy, const WgradTcParams p) {
+    const int C = CT > 0 ? CT : p.C;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     const int a_bytes = p.Qpad * 128;                   // dy tile: Qpad pixels x 64 filters
@@ -275,9 +282,10 @@ k_conv_tc_wgrad(const __grid_constant__ CUtensorMap map_dy, const WgradTcParams 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = p.n_img * p.P;                   // one dy row per tile
     const int SBO = p.KO * 128;                         // bytes between 8-row groups of the Hankel tile
+    const int nacc = p.nacc;                            // accumulators in use
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < NST; ++i) { bar_init(&S.full[i], 1); bar_init(&S.empty[i], 1); bar_init(&S.bready[i], 4); }
+        for (int i = 0; i < NST; ++i) { bar_init(&S.full[i], 1); bar_init(&S.empty[i], 1); bar_init(&S.bready[i], WT_BUILD_WARPS); }
         bar_init(&S.tdone, 1);
         fence_barrier_init();
     }
@@ -297,7 +305,7 @@ k_conv_tc_wgrad(const __grid_constant__ CUtensorMap map_dy, const WgradTcParams 
                 const int stage = it % NST;
                 const unsigned ph = (unsigned)(it / NST) & 1u;
                 const int n = tile / p.P, pr = tile % p.P;
-                bar_wait(&S.empty[stage], ph ^ 1u);
+                if (p.dbg & 128) bar_wait(&S.empty[stage], ph ^ 1u); else bar_wait_relaxed(&S.empty[stage], ph ^ 1u);
                 bar_expect_tx(&S.full[stage], (unsigned)(a_bytes + p.R * p.xrow_bytes));
                 tma_load_3d(A + (size_t)stage * a_bytes, &map_dy, 0, 0, tile, &S.full[stage]);     // pixels >= Q arrive as zeros
                 for (int r = 0; r < p.R; ++r)
@@ -307,19 +315,35 @@ k_conv_tc_wgrad(const __grid_constant__ CUtensorMap map_dy, const WgradTcParams 
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(64, p.nwin, /*A MN-major*/ 1, 0);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-                const int stage = it % NST;
-                const unsigned ph = (unsigned)(it / NST) & 1u;
+            // The issuing thread is a single dependent instruction stream: every extra instruction per tcgen05.mma shows up
+            // in the kernel time (measured: a loop body that rebuilt both descriptors cost ~140 clk per MMA and capped the
+            // kernel at 4.1 TB/s; without MMAs the same pipeline streams 6.3 TB/s).  So: descriptors are built once and
+            // advanced by constant adds, no divisions, no debug branches inside the loop.
+            const uint32_t idesc = umma_idesc_bf16((p.dbg & 8) ? 128 : 64, p.nwin, /*A MN-major*/ (p.dbg & 4) ? 0 : 1, 0);
+            const uint64_t adesc0 = (p.dbg & 4) ? umma_desc_k_sw128(s_u32(A)) : umma_desc_mn_sw128(s_u32(A));
+            const uint64_t bdesc0 = (p.dbg & 16) ? umma_desc_k_sw128(s_u32(B)) : umma_desc_k_none(s_u32(B), 128, (uint32_t)SBO);
+            const uint32_t a_step = (uint32_t)a_bytes >> 4, b_step = (uint32_t)b_bytes >> 4;   // descriptor address units of 16 B
+            const int nk = (p.dbg & 2) ? 0 : p.Qpad / 16;
+            int stage = 0;
+            unsigned ph = 0;
+            bool first = true;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 bar_wait(&S.full[stage], ph);
                 bar_wait(&S.bready[stage], ph);
                 tc_fence_after();
-                const uint32_t a0 = s_u32(A + (size_t)stage * a_bytes), b0 = s_u32(B + (size_t)stage * b_bytes);
-                for (int ks = 0; ks < p.Qpad / 16; ++ks)       // 16 pixels per MMA
-                    tc_mma_bf16(tmem, umma_desc_mn_sw128(a0 + ks * 2048), umma_desc_k_none(b0 + ks * 256, 128, (uint32_t)SBO), idesc,
-                                (it | ks) != 0 ? 1u : 0u);
+                uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * a_step), bd = bdesc0 + (uint64_t)((uint32_t)stage * b_step);
+                // one accumulator, loop-invariant TMEM address and predicate: the loop body is the MMA and two descriptor adds
+                if (nk > 0) {
+                    tc_mma_bf16(tmem, ad, bd, idesc, first ? 0u : 1u);
+                    for (int ks = 1; ks < nk; ++ks) {           // 16 pixels per MMA
+                        ad += 2048 >> 4;
+                        bd += 256 >> 4;
+                        tc_mma_bf16(tmem, ad, bd, idesc, 1u);
+                    }
+                }
+                first = false;
                 tc_commit(&S.empty[stage]);
+                if (++stage == NST) { stage = 0; ph ^= 1u; }
             }
             tc_commit(&S.tdone);
         }
@@ -330,16 +354,16 @@ k_conv_tc_wgrad(const __grid_constant__ CUtensorMap map_dy, const WgradTcParams 
         int src_off[WT_ITEMS], dst_off[WT_ITEMS], lim[WT_ITEMS];
 #pragma unroll
         for (int i = 0; i < WT_ITEMS; ++i) {
-            const int L = b + i * 128;
+            const int L = b + i * (32 * WT_BUILD_WARPS);
             src_off[i] = -1; dst_off[i] = 0; lim[i] = 0;
             if (L < units) {
                 const int n8 = L / (p.KO * 8), rem = L % (p.KO * 8), kk = rem >> 3, nl = rem & 7, n = n8 * 8 + nl;
                 if (n < p.nreal) {
                     const int r = n / p.SC, j = n % p.SC;
-                    const int e0 = kk * 8 * p.C + j;            // element of the x row feeding pixel 8*kk
+                    const int e0 = kk * 8 * C + j;              // element of the x row feeding pixel 8*kk
                     src_off[i] = r * p.xrow_stride + e0 * 2;
                     dst_off[i] = n8 * SBO + kk * 128 + nl * 16;
-                    lim[i] = p.W * p.C - e0;                    // elements of the row at or after e0
+                    lim[i] = p.W * C - e0;                      // elements of the row at or after e0
                 }
             }
         }
@@ -347,40 +371,59 @@ k_conv_tc_wgrad(const __grid_constant__ CUtensorMap map_dy, const WgradTcParams 
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int stage = it % NST;
             const unsigned ph = (unsigned)(it / NST) & 1u;
-            bar_wait(&S.full[stage], ph);
+            if (p.dbg & 128) bar_wait(&S.full[stage], ph); else bar_wait_relaxed(&S.full[stage], ph);
             const unsigned char *xs = X + (size_t)stage * x_bytes;
             unsigned char *bs = B + (size_t)stage * b_bytes;
+            unsigned short e[WT_ITEMS][8];
+            if (!(p.dbg & 1)) {
+#pragma unroll
+            for (int i = 0; i < WT_ITEMS; ++i) {                // all gathers in flight before the first use
+                const unsigned short *src = reinterpret_cast<const unsigned short *>(xs + (src_off[i] >= 0 ? src_off[i] : 0));
+#pragma unroll
+                for (int u = 0; u < 8; ++u) e[i][u] = src[u * C];
+            }
 #pragma unroll
             for (int i = 0; i < WT_ITEMS; ++i) {
                 if (src_off[i] >= 0) {
-                    const unsigned short *src = reinterpret_cast<const unsigned short *>(xs + src_off[i]);
-                    unsigned short e[8];
+                    if (p.guard) {
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) e[u] = (u * p.C < lim[i]) ? src[u * p.C] : (unsigned short)0;
+                        for (int u = 0; u < 8; ++u)
+                            if (u * C >= lim[i]) e[i][u] = 0;
+                    }
                     uint4 o;
-                    o.x = e[0] | ((uint32_t)e[1] << 16); o.y = e[2] | ((uint32_t)e[3] << 16);
-                    o.z = e[4] | ((uint32_t)e[5] << 16); o.w = e[6] | ((uint32_t)e[7] << 16);
+                    o.x = e[i][0] | ((uint32_t)e[i][1] << 16); o.y = e[i][2] | ((uint32_t)e[i][3] << 16);
+                    o.z = e[i][4] | ((uint32_t)e[i][5] << 16); o.w = e[i][6] | ((uint32_t)e[i][7] << 16);
                     *reinterpret_cast<uint4 *>(bs + dst_off[i]) = o;
                 }
+            }
             }
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) bar_arrive(&S.bready[stage]);
         }
+        if (warp >= 6) goto done;
         // ===== read-out: the raw accumulator lanes of this CTA =====
         bar_wait(&S.tdone, 0);
         tc_fence_after();
         const int quarter = warp & 3;
         float *dst = p.slots + ((size_t)blockIdx.x * 128 + quarter * 32 + lane) * p.nwin;
         for (int c0 = 0; c0 < p.nwin; c0 += 32) {
-            uint32_t v[32];
-            tc_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-            tc_wait_ld();
+            float sum[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[i] = 0.0f;
+            for (int a = 0; a < nacc; ++a) {
+                uint32_t v[32];
+                tc_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * p.acc_cols + c0), v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sum[i] += __uint_as_float(v[i]);
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                if (c0 + i < p.nwin) dst[c0 + i] = __uint_as_float(v[i]);
+                if (c0 + i < p.nwin) dst[c0 + i] = sum[i];
         }
     }
+done:
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -389,25 +432,21 @@ k_conv_tc_wgrad(const __grid_constant__ CUtensorMap map_dy, const WgradTcParams 
     }
 }
 
-// dw[k][n] = sum over CTAs of slots[cta][lane(k)][n]; an M = 64 accumulator keeps row k in TMEM lane (k / 16) * 32 + k % 16
+// dw[k][n] = sum over CTAs of slots[cta][lane(k)][n]; an M = 64 accumulator keeps row k in TMEM lane (k / 16) * 32 + k % 16.
+// One warp per output: lane l adds slots l, l + 32, ... in order, then a fixed butterfly -- deterministic.
 __global__ void k_conv_tc_wgrad_reduce(const float *__restrict__ slots, float *__restrict__ dw, int nslots, int K, int nreal, int nwin,
                                        int lane_map) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (o >= K * nreal) return;
     const int k = o / nreal, n = o % nreal;
     const int tl = lane_map == 0 ? (k / 16) * 32 + (k % 16) : (lane_map == 1 ? k : (k / 32) * 64 + (k % 32));
     const float *src = slots + (size_t)tl * nwin + n;
     const size_t step = (size_t)128 * nwin;
-    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-    int i = 0;
-    for (; i + 3 < nslots; i += 4) {
-        s0 += src[(size_t)i * step];
-        s1 += src[(size_t)(i + 1) * step];
-        s2 += src[(size_t)(i + 2) * step];
-        s3 += src[(size_t)(i + 3) * step];
-    }
-    for (; i < nslots; ++i) s0 += src[(size_t)i * step];
-    dw[o] = (s0 + s1) + (s2 + s3);
+    float s0 = 0.0f;
+    for (int i = lane; i < nslots; i += 32) s0 += src[(size_t)i * step];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) s0 += __shfl_xor_sync(0xFFFFFFFFu, s0, d);
+    if (lane == 0) dw[o] = s0;
 }
 
 int env_int(const char *name, int dflt) {
@@ -425,6 +464,22 @@ int launch_dgrad(pcnn_ctx *ctx, const CUtensorMap &map_dy, const CUtensorMap &ma
     k_conv_tc_dgrad<R, C><<<grid, DG_THREADS, smem, ctx->stream>>>(map_dy, map_b, p);
     PCNN_CHECK_LAUNCH(ctx);
     return PCNN_OK;
+}
+
+template <int CT>
+int launch_wgrad(pcnn_ctx *ctx, const CUtensorMap &map_dy, const WgradTcParams &p, int grid, size_t smem) {
+    static bool configured = false;
+    if (!configured) {
+        PCNN_CUDA(cudaFuncSetAttribute(k_conv_tc_wgrad<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BUDGET + 2048));
+        configured = true;
+    }
+    k_conv_tc_wgrad<CT><<<grid, WT_THREADS, smem, ctx->stream>>>(map_dy, p);
+    PCNN_CHECK_LAUNCH(ctx);
+    return PCNN_OK;
+}
+
+CUtensorMapL2promotion l2_promotion() {     // PCNN_TMA_L2PROMO=128|256 (default 256: a dy pixel is 128 B and its neighbour is next)
+    return env_int("PCNN_TMA_L2PROMO", 256) == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
 }
 
 }  // namespace
@@ -445,8 +500,8 @@ bool pcnn_conv_wgrad_tc_ok(int N, int H, int W, int C, int K, int R, int S, int 
     if (K != 64 || ((uintptr_t)dy & 15) || ((uintptr_t)x & 15) || row_pitch % 8) return false;
     const int Q = W - S + 1, Qpad = (Q + 15) / 16 * 16;
     const int nreal = R * S * C, nwin = (nreal + 15) / 16 * 16;
-    if (Qpad > 256 || nwin > 256) return false;
-    if (((nreal + 7) / 8) * 8 * (Qpad / 8) > WT_ITEMS * 128) return false;
+    if (Qpad > 256 || nwin > 512 / WT_NACC) return false;
+    if (((nreal + 7) / 8) * 8 * (Qpad / 8) > WT_ITEMS * 32 * WT_BUILD_WARPS) return false;
     const int xrow_stride = (((Qpad + S) * C * 2) + 127) / 128 * 128;
     const size_t stage = (size_t)Qpad * 128 + (size_t)nwin * Qpad * 2 + (size_t)R * xrow_stride;
     return 2 * stage + sizeof(WgradCtl) + 1024 <= (size_t)WT_SMEM_BUDGET && N > 0;
@@ -504,7 +559,7 @@ int pcnn_conv_dgrad_tc(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f32
 
     __nv_bfloat16 *T = nullptr;
     const size_t t_elems = (size_t)nvar * p.nwin * K;
-    PCNN_CUDA(cudaMallocAsync((void **)&T, t_elems * 2, ctx->stream));
+    { int rcs = pcnn_scratch(ctx, t_elems * 2, (void **)&T); if (rcs) return rcs; }
     k_dgrad_build_variants<<<(int)((t_elems + 255) / 256), 256, 0, ctx->stream>>>(filt_f32_dev, T, vm, nvar, p.nwin, K, R, S, C);
     PCNN_CHECK_LAUNCH(ctx);
 
@@ -513,8 +568,7 @@ int pcnn_conv_dgrad_tc(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f32
         const uint64_t dims[4] = {(uint64_t)K, (uint64_t)Q, (uint64_t)P, (uint64_t)N};
         const uint64_t str[3] = {(uint64_t)K * 2, (uint64_t)Q * K * 2, (uint64_t)P * Q * K * 2};
         const uint32_t box[4] = {64, 1, 32, 1};
-        int rc = make_map_bf16(&map_dy, const_cast<void *>(dy_bf16), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+        int rc = make_map_bf16(&map_dy, const_cast<void *>(dy_bf16), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion());
         if (rc) return rc;
         const uint64_t bd[2] = {(uint64_t)K, (uint64_t)nvar * p.nwin};
         const uint64_t bs[1] = {(uint64_t)K * 2};
@@ -529,7 +583,6 @@ int pcnn_conv_dgrad_tc(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f32
     else if (R == 3 && C == 4) rc = launch_dgrad<3, 4>(ctx, map_dy, map_b, p, grid, smem);
     else if (R == 5 && C == 1) rc = launch_dgrad<5, 1>(ctx, map_dy, map_b, p, grid, smem);
     else { pcnn_set_error("pcnn_conv_dgrad: no tensor-core instantiation for R = %d, C = %d", R, C); rc = PCNN_ERR_ARG; }
-    PCNN_CUDA(cudaFreeAsync(T, ctx->stream));
     return rc;
 }
 
@@ -543,8 +596,12 @@ int pcnn_conv_wgrad_tc(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16, f
     p.nwin = (p.nreal + 15) / 16 * 16;
     p.Qpad = (Q + 15) / 16 * 16;
     p.KO = p.Qpad / 8;
+    p.acc_cols = (p.nwin + 31) / 32 * 32;
+    p.nacc = 1;          // measured: rotating accumulators buys nothing (the MMA stream is issue-bound, not dependency-bound)
+    if (env_int("PCNN_WGRAD_NACC", 0) > 0 && env_int("PCNN_WGRAD_NACC", 0) < p.nacc) p.nacc = env_int("PCNN_WGRAD_NACC", 0);
     p.tmem_cols = 32;
-    while (p.tmem_cols < (p.nwin + 31) / 32 * 32) p.tmem_cols *= 2;
+    while (p.tmem_cols < p.nacc * p.acc_cols) p.tmem_cols *= 2;
+    if (env_int("PCNN_WGRAD_TMEMCOLS", 0) > p.tmem_cols) p.tmem_cols = env_int("PCNN_WGRAD_TMEMCOLS", 0);
     p.x_pitch = row_pitch > 0 ? row_pitch : W * C;
     p.x_image_rows = image_rows > 0 ? image_rows : H;
     p.xrow_bytes = (W * C * 2 + 15) / 16 * 16;
@@ -557,27 +614,24 @@ int pcnn_conv_wgrad_tc(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16, f
     const size_t smem = (size_t)p.stages * stage + sizeof(WgradCtl) + 1024;
     const long ntiles = (long)N * P;
     const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
-    PCNN_CUDA(cudaMallocAsync((void **)&p.slots, (size_t)grid * 128 * p.nwin * sizeof(float), ctx->stream));
+    { int rcs = pcnn_scratch(ctx, (size_t)grid * 128 * p.nwin * sizeof(float), (void **)&p.slots); if (rcs) return rcs; }
     CUtensorMap map_dy;
     {
         const uint64_t dims[3] = {(uint64_t)K, (uint64_t)Q, (uint64_t)N * P};
         const uint64_t str[2] = {(uint64_t)K * 2, (uint64_t)Q * K * 2};
         const uint32_t box[3] = {64, (uint32_t)p.Qpad, 1};
-        int rc = make_map_bf16(&map_dy, const_cast<void *>(dy_bf16), 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+        int rc = make_map_bf16(&map_dy, const_cast<void *>(dy_bf16), 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, l2_promotion());
         if (rc) return rc;
     }
-    static bool configured = false;
-    if (!configured) {
-        PCNN_CUDA(cudaFuncSetAttribute(k_conv_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM_BUDGET + 2048));
-        configured = true;
-    }
-    k_conv_tc_wgrad<<<grid, WT_THREADS, smem, ctx->stream>>>(map_dy, p);
-    PCNN_CHECK_LAUNCH(ctx);
+    p.guard = (W * C * 2) % 16 != 0;
+    p.dbg = env_int("PCNN_WGRAD_DBG", 0);
+    if (env_int("PCNN_WGRAD_STAGES", 0) > 1 && env_int("PCNN_WGRAD_STAGES", 0) < p.stages) p.stages = env_int("PCNN_WGRAD_STAGES", 0);
+    int rc = C == 3 ? launch_wgrad<3>(ctx, map_dy, p, grid, smem) : C == 1 ? launch_wgrad<1>(ctx, map_dy, p, grid, smem)
+           : C == 4 ? launch_wgrad<4>(ctx, map_dy, p, grid, smem) : launch_wgrad<0>(ctx, map_dy, p, grid, smem);
+    if (rc) return rc;
     const int nout = K * p.nreal;
-    k_conv_tc_wgrad_reduce<<<(nout + 127) / 128, 128, 0, ctx->stream>>>(p.slots, dw_f32, grid, K, p.nreal, p.nwin,
+    k_conv_tc_wgrad_reduce<<<(nout * 32 + 255) / 256, 256, 0, ctx->stream>>>(p.slots, dw_f32, grid, K, p.nreal, p.nwin,
                                                                         env_int("PCNN_WGRAD_LANEMAP", 0));
     PCNN_CHECK_LAUNCH(ctx);
-    PCNN_CUDA(cudaFreeAsync(p.slots, ctx->stream));
     return PCNN_OK;
 }

@@ -109,6 +109,7 @@ extern "C" int pcnn_destroy(pcnn_ctx *ctx) {
     pcnn_comm_destroy(ctx);
     pcnn_p2p_detach(ctx);
     if (ctx->p2p_base) cudaFree(ctx->p2p_base);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->d_trace) cudaFree(ctx->d_trace);
     if (ctx->d_bar) cudaFree(ctx->d_bar);
     if (ctx->d_abort) cudaFree(ctx->d_abort);
@@ -137,6 +138,20 @@ extern "C" int pcnn_destroy(pcnn_ctx *ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+    return PCNN_OK;
+}
+
+int pcnn_scratch(pcnn_ctx *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->scratch_bytes) {
+        PCNN_CUDA(cudaStreamSynchronize(ctx->stream));       // earlier work may still be using the old block
+        if (ctx->scratch) PCNN_CUDA(cudaFree(ctx->scratch));
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+        const size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        PCNN_CUDA(cudaMalloc(&ctx->scratch, want));
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
     return PCNN_OK;
 }
 

@@ -109,6 +109,10 @@ struct pcnn_ctx {
     uint2 *p2p_peer_inbox[PCNN_MAX_PEERS] = {};
     void *p2p_mapped[PCNN_MAX_PEERS] = {};
 
+    // grow-only device scratch of the convolution backward passes (partial sums, filter variants); stream-ordered reuse
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+
     long launches = 0;
 };
 
@@ -150,3 +154,6 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
 int pcnn_persist_check(pcnn_ctx *ctx);
 // comm.cu
 int pcnn_comm_allreduce_packed(pcnn_ctx *ctx);
+// pcnn_abi.cu: at least `bytes` of device scratch, valid until the next call that asks for more (work using it must be
+// enqueued on ctx->stream)
+int pcnn_scratch(pcnn_ctx *ctx, size_t bytes, void **out);

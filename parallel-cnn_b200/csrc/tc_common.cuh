@@ -30,6 +30,25 @@ __device__ __forceinline__ void bar_wait(unsigned long long *b, unsigned parity)
         "TC_DONE:\n"
         "}\n" ::"r"(s_u32(b)), "r"(parity) : "memory");
 }
+// Polling wait with back-off for warps that are NOT on the critical issue path (producers, operand builders, epilogues):
+// a tight try_wait loop competes for issue slots with the single thread that issues the tcgen05.mma stream whenever both
+// live on the same SM sub-partition (measured: spinning neighbours doubled the per-MMA issue interval).
+__device__ __forceinline__ void bar_wait_relaxed(unsigned long long *b, unsigned parity, unsigned sleep_ns = 64) {
+    for (;;) {
+        unsigned ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(s_u32(b)), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(sleep_ns);
+    }
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy shared-memory writes -> visible to the async proxy (TMA stores, tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -283,6 +283,16 @@ class Engine:
         self._call("pcnn_measure_fp32_peak", C.byref(t))
         return t.value
 
+    def measure_mma_rate(self, M, N, a_mn=0, b_mn=0, nacc=1, reps=2000):
+        t = C.c_float()
+        self._call("pcnn_measure_mma_rate", int(M), int(N), int(a_mn), int(b_mn), int(nacc), int(reps), C.byref(t))
+        return t.value
+
+    def measure_tma_read(self, dev_bf16, N, P, Q, mode, iters=10):
+        t = C.c_float()
+        self._call("pcnn_measure_tma_read", _p(dev_bf16), int(N), int(P), int(Q), int(mode), int(iters), C.byref(t))
+        return t.value
+
     # ------------------------------------------------------------------ data parallel
     @staticmethod
     def comm_unique_id():

@@ -69,13 +69,16 @@ def run_bwd(name, N, H, W, C, K, R, S, iters):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        import time
         e0.record(stream)
+        t0 = time.perf_counter()
         for _ in range(iters):
             fn()
+        host_us = (time.perf_counter() - t0) / iters * 1e6           # host time to enqueue one call
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
-        print(json.dumps({"case": name + " " + what, "N": N, "ms": ms, "img_per_s": N / (ms * 1e-3), "alg_GBps": alg / (ms * 1e-3) / 1e9,
+        print(json.dumps({"case": name + " " + what, "host_enqueue_us": host_us, "N": N, "ms": ms, "img_per_s": N / (ms * 1e-3), "alg_GBps": alg / (ms * 1e-3) / 1e9,
                           "hbm_frac": alg / (ms * 1e-3) / 1e9 / HBM, "useful_TFLOPs": flops / (ms * 1e-3) / 1e12,
                           "path": os.environ.get("PCNN_CONV_BWD", "tc"), "working_set_MB": alg / 1e6}), flush=True)
     del xb, dyb, dx
@@ -84,6 +87,8 @@ def run_bwd(name, N, H, W, C, K, R, S, iters):
 if only in ("all", "bwd"):
     for N in (8, 32, 128):
         run_bwd("224x224x3->64x3x3 bf16 (config 5)", N, 224, 224, 3, 64, 3, 3, 10)
+if only == "bwd128":                                                   # the profiler's target: few launches
+    run_bwd("224x224x3->64x3x3 bf16 (config 5)", 128, 224, 224, 3, 64, 3, 3, 2)
 if only in ("all", "lenet"):
     for N in (1024, 8192, 65536):
         run("lenet_c1_bf16_sigmoid (config 3 shape)", N, 28, 28, 1, 6, 5, 5, 1, 20)
