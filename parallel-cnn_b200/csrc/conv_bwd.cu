@@ -12,6 +12,10 @@
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
+// conv_dgrad_tc.cu
+bool pcnn_conv_dgrad_rows_ok(int N, int H, int W, int C, int K, int R, int S, const void *dy);
+int pcnn_conv_dgrad_rows(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f32_dev, void *dx_bf16, int N, int H, int W, int C, int K,
+                         int R, int S, int row_pitch, int image_rows);
 // conv_bwd_tc.cu
 bool pcnn_conv_dgrad_tc_ok(int N, int H, int W, int C, int K, int R, int S, const void *dy);
 bool pcnn_conv_wgrad_tc_ok(int N, int H, int W, int C, int K, int R, int S, int row_pitch, const void *x, const void *dy);
@@ -156,8 +160,13 @@ extern "C" int pcnn_conv_dgrad(pcnn_ctx *ctx, const void *dy_bf16, const float *
     ConvShape s;
     int rc = check_shape("pcnn_conv_dgrad", N, H, W, C, K, R, S, row_pitch, image_rows, &s);
     if (rc) return rc;
-    if (!force_fma() && pcnn_conv_dgrad_tc_ok(N, H, W, C, K, R, S, dy_bf16))
-        return pcnn_conv_dgrad_tc(ctx, dy_bf16, filt_f32_dev, dx_bf16, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
+    if (!force_fma()) {
+        const char *impl = getenv("PCNN_DGRAD_IMPL");            // "cols" = the pixel-column kernel of conv_bwd_tc.cu
+        if (!(impl && impl[0] == 'c') && pcnn_conv_dgrad_rows_ok(N, H, W, C, K, R, S, dy_bf16))
+            return pcnn_conv_dgrad_rows(ctx, dy_bf16, filt_f32_dev, dx_bf16, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
+        if (pcnn_conv_dgrad_tc_ok(N, H, W, C, K, R, S, dy_bf16))
+            return pcnn_conv_dgrad_tc(ctx, dy_bf16, filt_f32_dev, dx_bf16, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
+    }
     pcnn_device_guard g(ctx->device);
     const long total = (long)N * H * W * C;
     long blocks = (total + 255) / 256;

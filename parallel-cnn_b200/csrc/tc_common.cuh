@@ -115,6 +115,14 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 4 consecutive columns (the column address must be a multiple of 4)
+__device__ __forceinline__ void tc_ld_32x4(uint32_t taddr, uint32_t &v0, uint32_t &v1, uint32_t &v2, uint32_t &v3) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_st_zero_32x4(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(taddr), "r"(z) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // zero 32 lanes x 32 columns of TMEM (the accumulator of a kernel whose every MMA accumulates)
 __device__ __forceinline__ void tc_st_zero_32x32(uint32_t taddr) {
