@@ -1,7 +1,7 @@
 // parallel-cnn_b200/csrc/conv_bwd.cu -- weight- and input-gradient of the generic NHWC bf16 convolution.
 //
 // Entry points + the general-shape kernels on the fp32 FMA pipe (bf16 operands, fp32 accumulation, deterministic two-stage
-// reduction, no atomics).  Shapes the tensor cores can take (64 filters; see conv_bwd_tc.cu) are routed to the tcgen05
+// reduction, no atomics).  Shapes the tensor cores can take (64 filters; conv_wgrad_tc.cu, conv_dgrad_tc.cu) are routed to the tcgen05
 // kernels, which are the roofline path: both passes move the same 6.6 MB/image as the forward pass (config 5) and are
 // HBM-bound at 170 MFLOP per 6.6 MB, which the FMA pipe cannot sustain.  PCNN_CONV_BWD=fma forces the
 // FMA-pipe kernels (used by the tests to check both paths against the oracle).
@@ -16,14 +16,10 @@
 bool pcnn_conv_dgrad_rows_ok(int N, int H, int W, int C, int K, int R, int S, const void *dy);
 int pcnn_conv_dgrad_rows(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f32_dev, void *dx_bf16, int N, int H, int W, int C, int K,
                          int R, int S, int row_pitch, int image_rows);
-// conv_bwd_tc.cu
-bool pcnn_conv_dgrad_tc_ok(int N, int H, int W, int C, int K, int R, int S, const void *dy);
-bool pcnn_conv_wgrad_tc_ok(int N, int H, int W, int C, int K, int R, int S, int row_pitch, const void *x, const void *dy);
-int pcnn_conv_dgrad_tc(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f32_dev, void *dx_bf16, int N, int H, int W, int C,
-                       int K, int R, int S, int row_pitch, int image_rows);
-int pcnn_conv_wgrad_tc(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16, float *dw_f32, int N, int H, int W, int C, int K,
-                       int R, int S, int row_pitch, int image_rows);
-
+// conv_wgrad_tc.cu
+bool pcnn_conv_wgrad_rows_ok(int N, int H, int W, int C, int K, int R, int S, int row_pitch, const void *x, const void *dy);
+int pcnn_conv_wgrad_rows(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16, float *dw_f32, int N, int H, int W, int C, int K,
+                         int R, int S, int row_pitch, int image_rows);
 namespace {
 
 bool force_fma() {
@@ -137,8 +133,8 @@ extern "C" int pcnn_conv_wgrad(pcnn_ctx *ctx, const void *x_bf16, const void *dy
     ConvShape s;
     int rc = check_shape("pcnn_conv_wgrad", N, H, W, C, K, R, S, row_pitch, image_rows, &s);
     if (rc) return rc;
-    if (!force_fma() && pcnn_conv_wgrad_tc_ok(N, H, W, C, K, R, S, s.row_pitch, x_bf16, dy_bf16))
-        return pcnn_conv_wgrad_tc(ctx, x_bf16, dy_bf16, dw_f32, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
+    if (!force_fma() && pcnn_conv_wgrad_rows_ok(N, H, W, C, K, R, S, s.row_pitch, x_bf16, dy_bf16))
+        return pcnn_conv_wgrad_rows(ctx, x_bf16, dy_bf16, dw_f32, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
     const int nout = K * R * S * C;
     PCNN_REQUIRE(nout <= WG_THREADS * WG_MAXO, PCNN_ERR_ARG, "pcnn_conv_wgrad: K*R*S*C = %d exceeds %d", nout, WG_THREADS * WG_MAXO);
     pcnn_device_guard g(ctx->device);
@@ -160,13 +156,8 @@ extern "C" int pcnn_conv_dgrad(pcnn_ctx *ctx, const void *dy_bf16, const float *
     ConvShape s;
     int rc = check_shape("pcnn_conv_dgrad", N, H, W, C, K, R, S, row_pitch, image_rows, &s);
     if (rc) return rc;
-    if (!force_fma()) {
-        const char *impl = getenv("PCNN_DGRAD_IMPL");            // "cols" = the pixel-column kernel of conv_bwd_tc.cu
-        if (!(impl && impl[0] == 'c') && pcnn_conv_dgrad_rows_ok(N, H, W, C, K, R, S, dy_bf16))
-            return pcnn_conv_dgrad_rows(ctx, dy_bf16, filt_f32_dev, dx_bf16, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
-        if (pcnn_conv_dgrad_tc_ok(N, H, W, C, K, R, S, dy_bf16))
-            return pcnn_conv_dgrad_tc(ctx, dy_bf16, filt_f32_dev, dx_bf16, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
-    }
+    if (!force_fma() && pcnn_conv_dgrad_rows_ok(N, H, W, C, K, R, S, dy_bf16))
+        return pcnn_conv_dgrad_rows(ctx, dy_bf16, filt_f32_dev, dx_bf16, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
     pcnn_device_guard g(ctx->device);
     const long total = (long)N * H * W * C;
     long blocks = (total + 255) / 256;

@@ -2,10 +2,10 @@
 //
 //     dx[n][h][w][c] = sum_{k,r,s} dy[n][h-r][w-s][k] * f[k][r][s][c]
 //
-// Why a second formulation: the pixel-column kernel of conv_bwd_tc.cu gathers 128-byte pieces of 128 different dy rows per
-// TMA box; a TMA pipeline with that access pattern tops out at 3.6-4.4 TB/s on B200 (pcnn_measure_tma_read, mode 2) against
-// 6.7-7.1 TB/s for contiguous boxes, and the kernel sat exactly on that ceiling.  Here every TMA box is a contiguous run of
-// one dy row:
+// Access pattern first: a first version put 128 dy ROWS of one pixel column on the TMEM lanes (col2im folded into the TMEM
+// column offset); its TMA boxes gathered 128-byte pieces of 128 different rows, and a TMA pipeline with that pattern tops
+// out at 3.6-4.4 TB/s on B200 (pcnn_measure_tma_read, mode 2) against 6.7-7.1 TB/s for contiguous boxes -- the kernel sat
+// exactly on that ceiling (4.6 TB/s, profiles/r01_README.md).  Here every TMA box is a contiguous run of one dy row:
 //   * A CTA owns a strip of <= 120 output columns and walks DOWN the rows of its share of the images.  One dy row of the
 //     strip is an A operand [128 pixels x 64 channels] (4 boxes of <= 32 pixels, one per TMEM lane quarter, overlapping by
 //     S-1 pixels so that the shift along s never crosses a warp).
@@ -17,6 +17,8 @@
 //   * Flow control is per group of 8 slots (tcgen05.commit -> tfull, epilogue -> tempty), NG groups in flight.
 //   * A CTA's share starts mid-image in general: the R-1 rows above it are replayed with filter variants that keep only the
 //     contributions landing inside the share (0.5 % extra reads at config 5).
+// TMEM addressing: the accumulator window of a tcgen05.mma must start on a multiple of 4 columns (an arbitrary column faults
+// with "misaligned address" on B200), hence SCP = 4*ceil(S*C/4) columns per slot.
 // Issue budget (pcnn_measure_mma_rate): one tcgen05.mma of N <= 112 occupies the issue/tensor path ~56-70 clk whatever its
 // size, so 4 MMAs per 15 KB of dy fit under the ~630 clk of HBM time those bytes cost one SM.
 #include "tc_common.cuh"
@@ -29,7 +31,7 @@ namespace {
 
 constexpr int D2_THREADS = 192;          // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (lane quarters)
 constexpr int D2_STAGE_BYTES = 16384;    // 4 quarters x 32 pixel rows x 128 B
-constexpr int D2_MAX_STAGES = 8;
+constexpr int D2_MAX_STAGES = 11;
 constexpr int D2_MAX_NG = 6;
 constexpr int D2_GROUP = 8;
 constexpr int D2_SMEM_BUDGET = 200 * 1024;

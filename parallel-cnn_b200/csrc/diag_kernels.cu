@@ -1,6 +1,6 @@
 // parallel-cnn_b200/csrc/diag_kernels.cu -- measurement helper: how fast can one SM-resident TMA pipeline stream a bf16 tensor
 // [N][P][Q][64] out of HBM with the box shapes the convolution kernels use?  The kernel is the load pipeline of
-// conv_bwd_tc.cu with the tensor-core work removed (the consumer releases every stage as soon as it lands), so its rate
+// the convolution backward kernels with the tensor-core work removed (the consumer releases every stage as soon as it lands), so its rate
 // is the ceiling those kernels can reach with that access pattern; bench scripts print it next to the kernels' own rate.
 #include "tc_common.cuh"
 

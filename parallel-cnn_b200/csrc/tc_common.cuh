@@ -1,5 +1,5 @@
 // parallel-cnn_b200/csrc/tc_common.cuh -- PTX wrappers (mbarrier, TMA, tcgen05, TMEM) and tensor-map helpers shared by the
-// tensor-core convolution kernels (conv_tc.cu forward, conv_bwd_tc.cu input- and weight-gradient).  sm_100a only.
+// tensor-core convolution kernels (conv_tc.cu forward, conv_dgrad_tc.cu input gradient, conv_wgrad_tc.cu weight gradient).  sm_100a only.
 #pragma once
 #include "pcnn_internal.h"
 

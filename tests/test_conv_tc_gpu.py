@@ -168,7 +168,7 @@ BWD_TC_SHAPES = [(1, 224, 224, 3, 64, 3, 3),      # config 5
 
 @pytest.mark.parametrize("shape", BWD_TC_SHAPES)
 def test_tensor_core_wgrad_and_dgrad_vs_oracle_and_fma_path(eng, pkg, shape, monkeypatch):
-    """The tcgen05 backward kernels (csrc/conv_bwd_tc.cu; 64 filters) against the oracle on the same bf16-rounded operands, and
+    """The tcgen05 backward kernels (csrc/conv_wgrad_tc.cu, csrc/conv_dgrad_tc.cu; 64 filters) against the oracle on the same bf16-rounded operands, and
     against the FMA-pipe kernels of csrc/conv_bwd.cu (PCNN_CONV_BWD=fma).  fp32 accumulation everywhere:
     wgrad rel-L2 <= 1e-5 vs the oracle; dgrad |d| <= 2^-8 |ref| + 1e-3 (one bf16 rounding of the result)."""
     N, H, W, C, K, R, S = shape
