@@ -149,6 +149,49 @@ def run_reference_arm(a):
 
 
 # ----------------------------------------------------------------------------------------------- our arm
+def conv_roofline(eng, pkg, stream, hbm_peak, peak_src, n_img=128, iters=10):
+    """BASELINE.json's second metric: HBM GB/s of the conv forward + weight gradient + input gradient against the roofline, on
+    configs[4] (synthetic 224x224x3 -> 64 filters 3x3, bf16 NHWC, valid padding; SURVEY.md 8d: 6,609,408 algorithmic bytes per
+    image per pass).  Every pass streams 846 MB (> 126 MB L2); CUDA events on the engine's stream, 3 warm-up launches."""
+    N, H, W, C, K, R, S = n_img, 224, 224, 3, 64, 3, 3
+    P, Q = H - R + 1, W - S + 1
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    x = (torch.rand((N, H, W, C), device="cuda", generator=g)).to(torch.bfloat16)                 # x ~ U[0,1)
+    f = torch.rand((K, R, S, C), device="cuda", generator=g) - 0.5                                 # w ~ U[-0.5,0.5)
+    yb = torch.empty((N, P, Q, K), dtype=torch.bfloat16, device="cuda")
+    dw = torch.empty((K, R, S, C), dtype=torch.float32, device="cuda")
+    dx = torch.empty((N, H, W, C), dtype=torch.bfloat16, device="cuda")
+    plan = pkg.ConvPlan(eng, N, H, W, C, K, R, S, f.cpu().numpy(), None, act=0, row_pitch=W * C)
+    alg = N * (H * W * C + P * Q * K) * 2
+    out = {}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    ms_f = timed(lambda: plan.fwd(x, yb))
+    dy = yb                                                                                        # the forward output doubles as dy
+    ms_w = timed(lambda: eng.conv_wgrad(x, dy, dw, N, H, W, C, K, R, S))
+    ms_d = timed(lambda: eng.conv_dgrad(dy, f, dx, N, H, W, C, K, R, S))
+    plan.close()
+    for name, ms in (("fwd", ms_f), ("wgrad", ms_w), ("dgrad", ms_d)):
+        gb = alg / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "GBps": gb, "frac": gb / hbm_peak}
+    tot = ms_f + ms_w + ms_d
+    gb = 3 * alg / (tot * 1e-3) / 1e9
+    return {"workload": "conv 224x224x3 -> 64x3x3, bf16 NHWC, tcgen05 kernels (BASELINE.json configs[4])", "images": N,
+            "algorithmic_bytes_per_pass": alg, "passes": out, "fwd_bwd": {"ms": tot, "GBps": gb, "frac": gb / hbm_peak},
+            "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "l2": "846 MB per pass, larger than L2"}
+
+
 def run_ours(a):
     import torch
     import pcnn_loader
@@ -291,6 +334,9 @@ def run_ours(a):
             cpu = {"value": v, "unit": "images/s", "cores": 1, "kind": kind,
                    "sample": f"{n_cpu} synthetic samples, Sequential/Main.cpp learn() loop (batch 1), {secs:.1f} s",
                    "host_cores_available": os.cpu_count()}
+        conv = None
+        if world == 1 and not a.no_conv:
+            conv = conv_roofline(eng, pkg, stream, hbm_peak, peak_src)
         line = {
             "metric": "MNIST training images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
@@ -304,6 +350,7 @@ def run_ours(a):
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * 785 * world,
                     "d2h_bytes_per_step": 4 * world, "steps": K2, "api": "Engine.learn_host (pcnn_learn_host), pinned host u8"},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "conv": conv,
         }
         print(json.dumps(line), flush=True)
     eng.close()
@@ -320,6 +367,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step (BASELINE.json configs[1]: 256)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-conv", action="store_true", help="skip the conv fwd+bwd roofline block (N = 1 only)")
     ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent"],
                     help="auto/persistent: one cooperative kernel runs all K steps (N > 1: in-kernel NVLink exchange); "
                          "graph: per-step kernels replayed from CUDA graphs (N > 1: ncclAllReduce per step)")

@@ -222,3 +222,16 @@ def test_tensor_core_dgrad_honours_row_and_image_pitch(eng, pkg):
     got = pkg.bf16_bits_to_f32(out[:, :H, :W * C].reshape(N, H, W, C))
     assert np.all(np.abs(got - dx_ref) <= 2.0 ** -8 * np.abs(dx_ref) + 1e-3)
     assert np.all(out[:, H:, :] == 0x4242) and np.all(out[:, :, W * C:] == 0x4242)
+
+
+def test_measurement_probes_report_sane_rates(eng, pkg):
+    """pcnn_measure_mma_rate / pcnn_measure_tma_read (the tables DESIGN.md 3.7 designs against): one small tcgen05.mma costs tens
+    of clocks, not hundreds; a TMA pipeline with contiguous boxes streams well above 1 TB/s and faster than the row-gather one."""
+    clk = eng.measure_mma_rate(128, 64, 0, 0, 1, 2000)
+    assert 30.0 < clk < 200.0, clk
+    assert eng.measure_mma_rate(128, 256, 0, 0, 1, 2000) > 1.5 * clk         # N = 256 runs at the tensor-pipe peak (128 clk)
+    N, P, Q = 16, 222, 222
+    buf = eng.array((N, P, Q, 64), np.uint16)
+    contiguous = eng.measure_tma_read(buf, N, P, Q, 3, 5)
+    gather = eng.measure_tma_read(buf, N, P, Q, 2, 5)
+    assert contiguous > 1000.0 and gather > 300.0 and contiguous > gather, (contiguous, gather)
