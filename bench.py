@@ -153,6 +153,7 @@ def conv_roofline(eng, pkg, stream, hbm_peak, peak_src, n_img=128, iters=10):
     """BASELINE.json's second metric: HBM GB/s of the conv forward + weight gradient + input gradient against the roofline, on
     configs[4] (synthetic 224x224x3 -> 64 filters 3x3, bf16 NHWC, valid padding; SURVEY.md 8d: 6,609,408 algorithmic bytes per
     image per pass).  Every pass streams 846 MB (> 126 MB L2); CUDA events on the engine's stream, 3 warm-up launches."""
+    import torch
     N, H, W, C, K, R, S = n_img, 224, 224, 3, 64, 3, 3
     P, Q = H - R + 1, W - S + 1
     g = torch.Generator(device="cuda").manual_seed(1234)
