@@ -52,13 +52,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 // 1 / (1 + e^-v) = 1 / (1 + 2^(-v log2 e)): MUFU.EX2 + MUFU.RCP.  The exponent product is rounded to fp32, so the
 // relative error of e^-v grows like |v| * 6e-8 (|v| < 30 here); the sigmoid inherits at most (1 - sigma) of it.
 __device__ __forceinline__ float sigmoid_fast(float v) {
-#ifdef PCNN_BISECT_OLD_SIGMOID
-    return __fdividef(1.0f, 1.0f + expf(-v));
-#else
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
     return __fdividef(1.0f, 1.0f + e);
-#endif
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
