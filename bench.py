@@ -316,7 +316,11 @@ def run_ours(a):
         frac_f, frac_h = tf / fp32_peak, gbs / hbm_peak
         roof = {"bound": "fp32_fma" if frac_f >= frac_h else "hbm",
                 "achieved": tf if frac_f >= frac_h else gbs, "peak": fp32_peak if frac_f >= frac_h else hbm_peak,
-                "unit": "TFLOP/s" if frac_f >= frac_h else "GB/s", "frac": max(frac_f, frac_h), "traffic": None,
+                "unit": "TFLOP/s" if frac_f >= frac_h else "GB/s", "frac": max(frac_f, frac_h),
+                # dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed `ncu --set full` captures
+                # (profiles/r01_persist_b256_ncu_full_subset.csv: 52.23 MB per 256-step launch at B = 256;
+                #  profiles/r01_fused_b256_ncu_full_subset.csv: 249.9 KB per k_fused launch), scaled to this launch
+                "traffic": (launch_steps * 204035.0 if persistent else 249900.0) if B == 256 else None,
                 "kernel": kernel, "kernel_ms": launch_ms,
                 "fp32": {"achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": frac_f,
                          "peak_source": "measured live (pcnn_measure_fp32_peak FFMA micro-benchmark)"},
