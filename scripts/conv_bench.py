@@ -94,6 +94,8 @@ if only in ("all", "lenet"):
         run("lenet_c1_bf16_sigmoid (config 3 shape)", N, 28, 28, 1, 6, 5, 5, 1, 20)
     for N in (8192, 65536):
         run("lenet_c1_bf16_sigmoid, 32-row image pitch (TMA-store epilogue)", N, 28, 28, 1, 6, 5, 5, 1, 20, image_rows=32)
+if only == "lenet1024":                                                # BASELINE configs[2]: LeNet c1 shape, batch 1024
+    run("lenet_c1_bf16_sigmoid (config 3 shape)", 1024, 28, 28, 1, 6, 5, 5, 1, 2)
 if only == "fwd128":                                                   # the profiler's target
     run("224x224x3->64x3x3 bf16 (config 5)", 128, 224, 224, 3, 64, 3, 3, 0, 2)
 if only in ("all", "cfg5"):
