@@ -167,3 +167,73 @@ extern "C" int pcnn_conv_dgrad(pcnn_ctx *ctx, const void *dy_bf16, const float *
     PCNN_CHECK_LAUNCH(ctx);
     return PCNN_OK;
 }
+
+// ---- zero padding around NHWC bf16 images (the "same"-padding front-end of the valid-padding kernels) ----
+namespace {
+
+// dst[n][h + ph][(w + pw) * C + c] = src[n][h][w][c]; everything else of the [dst_image_rows x dst_pitch] canvas = 0.
+// One thread per 2 destination elements (4-byte stores); rows are walked by a grid-stride loop.
+__global__ void __launch_bounds__(256) k_pad_nhwc(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int N, int H,
+                                                  int W, int C, int ph, int pw, int dst_pitch, int dst_image_rows) {
+    const long total = (long)N * dst_image_rows * dst_pitch;
+    const int wc = W * C, off = pw * C;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % dst_pitch);
+        const long row = i / dst_pitch;
+        const int r = (int)(row % dst_image_rows), n = (int)(row / dst_image_rows);
+        const int h = r - ph, e = col - off;
+        __nv_bfloat16 v = __float2bfloat16_rn(0.0f);
+        if (h >= 0 && h < H && e >= 0 && e < wc) v = src[((long)n * H + h) * wc + e];
+        dst[i] = v;
+    }
+}
+// the inverse: dst[n][h][w][c] = src[n][h + ph][(w + pw) * C + c]
+__global__ void __launch_bounds__(256) k_crop_nhwc(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__restrict__ dst, int N, int H,
+                                                   int W, int C, int ph, int pw, int src_pitch, int src_image_rows) {
+    const int wc = W * C;
+    const long total = (long)N * H * wc;
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const int e = (int)(i % wc);
+        const long row = i / wc;
+        const int h = (int)(row % H), n = (int)(row / H);
+        dst[i] = src[((long)n * src_image_rows + h + ph) * src_pitch + pw * C + e];
+    }
+}
+
+}  // namespace
+
+extern "C" int pcnn_pad_nhwc_bf16(pcnn_ctx *ctx, const void *src_bf16, void *dst_bf16, int N, int H, int W, int C, int pad_h, int pad_w,
+                                  int dst_row_pitch, int dst_image_rows) {
+    PCNN_REQUIRE(ctx && src_bf16 && dst_bf16 && N > 0 && H > 0 && W > 0 && C > 0 && pad_h >= 0 && pad_w >= 0, PCNN_ERR_ARG,
+                 "pcnn_pad_nhwc_bf16: bad argument");
+    if (dst_row_pitch <= 0) dst_row_pitch = (W + 2 * pad_w) * C;
+    if (dst_image_rows <= 0) dst_image_rows = H + 2 * pad_h;
+    PCNN_REQUIRE(dst_row_pitch >= (W + 2 * pad_w) * C && dst_image_rows >= H + 2 * pad_h, PCNN_ERR_ARG,
+                 "pcnn_pad_nhwc_bf16: destination canvas smaller than the padded image");
+    pcnn_device_guard g(ctx->device);
+    const long total = (long)N * dst_image_rows * dst_row_pitch;
+    long blocks = (total + 255) / 256;
+    if (blocks > (long)ctx->sm_count * 16) blocks = (long)ctx->sm_count * 16;
+    k_pad_nhwc<<<(int)blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const __nv_bfloat16 *>(src_bf16), reinterpret_cast<__nv_bfloat16 *>(dst_bf16),
+                                                    N, H, W, C, pad_h, pad_w, dst_row_pitch, dst_image_rows);
+    PCNN_CHECK_LAUNCH(ctx);
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_crop_nhwc_bf16(pcnn_ctx *ctx, const void *src_bf16, void *dst_bf16, int N, int H, int W, int C, int pad_h, int pad_w,
+                                   int src_row_pitch, int src_image_rows) {
+    PCNN_REQUIRE(ctx && src_bf16 && dst_bf16 && N > 0 && H > 0 && W > 0 && C > 0 && pad_h >= 0 && pad_w >= 0, PCNN_ERR_ARG,
+                 "pcnn_crop_nhwc_bf16: bad argument");
+    if (src_row_pitch <= 0) src_row_pitch = (W + 2 * pad_w) * C;
+    if (src_image_rows <= 0) src_image_rows = H + 2 * pad_h;
+    PCNN_REQUIRE(src_row_pitch >= (W + 2 * pad_w) * C && src_image_rows >= H + 2 * pad_h, PCNN_ERR_ARG,
+                 "pcnn_crop_nhwc_bf16: source canvas smaller than the padded image");
+    pcnn_device_guard g(ctx->device);
+    const long total = (long)N * H * W * C;
+    long blocks = (total + 255) / 256;
+    if (blocks > (long)ctx->sm_count * 16) blocks = (long)ctx->sm_count * 16;
+    k_crop_nhwc<<<(int)blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const __nv_bfloat16 *>(src_bf16), reinterpret_cast<__nv_bfloat16 *>(dst_bf16),
+                                                     N, H, W, C, pad_h, pad_w, src_row_pitch, src_image_rows);
+    PCNN_CHECK_LAUNCH(ctx);
+    return PCNN_OK;
+}

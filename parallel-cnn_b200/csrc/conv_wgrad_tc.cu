@@ -40,7 +40,6 @@ struct Wgrad2Params {
     long long x_pitch, x_image_rows;
     int xseg_bytes, xseg_stride, xrow_bytes;   // bytes wanted per x segment, smem stride, copyable bytes per x row
     int guard;                             // 1: the copied rows carry pad elements past W*C that must read as zero
-    int dbg;                               // timing experiments (PCNN_WGRAD_DBG): 1 tight polling, 2 no MMAs, 4 no Hankel build, 8 no x copies
     const __nv_bfloat16 *x;
     float *slots;                          // [grid][64 * nout]
 };
@@ -113,8 +112,7 @@ k_conv_tc_wgrad_rows(const __grid_constant__ CUtensorMap map_dy, const Wgrad2Par
                 const int xb = xseg_copy_bytes(p, ch);
                 int nx = p.H - p0;                        // x rows p0 .. p0 + NXR - 1 that exist
                 if (nx > p.NXR) nx = p.NXR;
-                if (p.dbg & 1) bar_wait(&S.empty[stage], ph ^ 1u); else bar_wait_relaxed(&S.empty[stage], ph ^ 1u, 32);
-                if (p.dbg & 8) nx = 0;
+                bar_wait_relaxed(&S.empty[stage], ph ^ 1u, 32);
                 bar_expect_tx(&S.full[stage], (unsigned)(dy_bytes + nx * xb));
                 tma_load_4d(DY + (size_t)stage * dy_bytes, &map_dy, 0, ch * p.PC, p0, n, &S.full[stage]);   // rows >= P, pixels >= Q: zeros
                 if (xb > 0)
@@ -136,14 +134,13 @@ k_conv_tc_wgrad_rows(const __grid_constant__ CUtensorMap map_dy, const Wgrad2Par
             int stage = 0;
             unsigned ph = 0;
             bool first = true;
-            const bool no_mma = (p.dbg & 2) != 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 bar_wait(&S.full[stage], ph);
                 bar_wait(&S.bready[stage], ph);
                 tc_fence_after();
                 uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * a_step), bd = bdesc0 + (uint64_t)((uint32_t)stage * b_step);
-                if (!no_mma) tc_mma_bf16(tmem, ad, bd, idesc, first ? 0u : 1u);
-                for (int ks = 1; ks < nk && !no_mma; ++ks) {
+                tc_mma_bf16(tmem, ad, bd, idesc, first ? 0u : 1u);
+                for (int ks = 1; ks < nk; ++ks) {
                     ad += 256 >> 4;                          // 16 pixels of the Hankel tile: two 128-byte core matrices
                     bd += 2048 >> 4;                         // 16 pixels of dy: two 1024-byte swizzle groups
                     tc_mma_bf16(tmem, ad, bd, idesc, 1u);
@@ -177,10 +174,9 @@ k_conv_tc_wgrad_rows(const __grid_constant__ CUtensorMap map_dy, const Wgrad2Par
         int stage = 0;
         unsigned ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            if (p.dbg & 1) bar_wait(&S.full[stage], ph); else bar_wait_relaxed(&S.full[stage], ph, 32);
+            bar_wait_relaxed(&S.full[stage], ph, 32);
             const uint32_t xs = x_s + (uint32_t)(stage * x_bytes), hs = hk_s + (uint32_t)(stage * hk_bytes);
             unsigned short e[W2_ITEMS][8];
-            if (!(p.dbg & 4)) {
 #pragma unroll
             for (int i = 0; i < W2_ITEMS; ++i) {             // all gathers in flight before the first use
                 const uint32_t src = xs + (uint32_t)(src_off[i] >= 0 ? src_off[i] : 0);
@@ -202,7 +198,6 @@ k_conv_tc_wgrad_rows(const __grid_constant__ CUtensorMap map_dy, const Wgrad2Par
                     o.z = e[i][4] | ((uint32_t)e[i][5] << 16); o.w = e[i][6] | ((uint32_t)e[i][7] << 16);
                     sts_v4(hs + (uint32_t)dst_off[i], o);
                 }
-            }
             }
             fence_proxy_async_smem();
             __syncwarp();
@@ -341,7 +336,6 @@ int pcnn_conv_wgrad_rows(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16,
     p.xrow_bytes = (W * C * 2 + 15) / 16 * 16;
     PCNN_REQUIRE((long long)p.xrow_bytes <= p.x_pitch * 2 && p.xseg_bytes <= p.xseg_stride, PCNN_ERR_ARG, "pcnn_conv_wgrad: row pitch");
     p.guard = (W * C * 2) % 16 != 0;
-    p.dbg = env_i("PCNN_WGRAD_DBG", 0);
     p.x = reinterpret_cast<const __nv_bfloat16 *>(x_bf16);
     const long ntiles = (long)N * p.n_pb * p.n_ch;
     const int grid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);

@@ -348,6 +348,12 @@ class Engine:
     def conv_dgrad(self, dy_bf16, filt_f32, dx_bf16, N, H, W, Cin, K, R, S, row_pitch=0, image_rows=0):
         self._call("pcnn_conv_dgrad", _p(dy_bf16), _p(filt_f32), _p(dx_bf16), N, H, W, Cin, K, R, S, int(row_pitch), int(image_rows))
 
+    def pad_nhwc(self, src_bf16, dst_bf16, N, H, W, Cin, pad_h, pad_w, dst_row_pitch=0, dst_image_rows=0):
+        self._call("pcnn_pad_nhwc_bf16", _p(src_bf16), _p(dst_bf16), N, H, W, Cin, int(pad_h), int(pad_w), int(dst_row_pitch), int(dst_image_rows))
+
+    def crop_nhwc(self, src_bf16, dst_bf16, N, H, W, Cin, pad_h, pad_w, src_row_pitch=0, src_image_rows=0):
+        self._call("pcnn_crop_nhwc_bf16", _p(src_bf16), _p(dst_bf16), N, H, W, Cin, int(pad_h), int(pad_w), int(src_row_pitch), int(src_image_rows))
+
     def softmax_ce(self, logits, labels, B, n, prob=None, d=None, loss=None):
         self._call("pcnn_softmax_ce", _p(logits), _p(labels), int(B), int(n), _p(prob), _p(d), _p(loss))
 

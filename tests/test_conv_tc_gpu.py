@@ -235,3 +235,49 @@ def test_measurement_probes_report_sane_rates(eng, pkg):
     contiguous = eng.measure_tma_read(buf, N, P, Q, 3, 5)
     gather = eng.measure_tma_read(buf, N, P, Q, 2, 5)
     assert contiguous > 1000.0 and gather > 300.0 and contiguous > gather, (contiguous, gather)
+
+
+def test_same_padding_convolution_through_pad_and_crop(eng, pkg):
+    """a 'same' (zero padded) 3x3 convolution, its weight gradient and its input gradient through
+    pcnn_pad_nhwc_bf16 / pcnn_crop_nhwc_bf16 around the valid-padding tensor-core kernels, against the oracle evaluated on
+    the host-padded tensors (tolerances as in the valid-padding tests)."""
+    N, H, W, C, K, R, S, pad = 2, 30, 40, 3, 64, 3, 3, 1
+    Hp, Wp = H + 2 * pad, W + 2 * pad
+    rng = np.random.default_rng(11)
+    x = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(rng.uniform(0, 1, (N, H, W, C)).astype(np.float32)))
+    f = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(rng.uniform(-0.5, 0.5, (K, R, S, C)).astype(np.float32)))
+    dy = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(rng.uniform(-1, 1, (N, H, W, K)).astype(np.float32)))      # same padding: P x Q = H x W
+    xp = np.zeros((N, Hp, Wp, C), np.float32)
+    xp[:, pad:pad + H, pad:pad + W, :] = x
+    y_ref = np.empty((N, H, W, K), np.float32)
+    dw_ref = np.empty((K, R, S, C), np.float32)
+    dxp_ref = np.empty((N, Hp, Wp, C), np.float32)
+    zero_b = np.zeros(K, np.float32)
+    O.oracle().orc_conv_fwd_nhwc(O.fp(xp.reshape(-1)), O.fp(f.reshape(-1)), O.fp(zero_b), O.fp(y_ref.reshape(-1)), N, Hp, Wp, C, K, R, S)
+    O.oracle().orc_conv_wgrad_nhwc(O.fp(xp.reshape(-1)), O.fp(dy.reshape(-1)), O.fp(dw_ref.reshape(-1)), N, Hp, Wp, C, K, R, S)
+    O.oracle().orc_conv_dgrad_nhwc(O.fp(dy.reshape(-1)), O.fp(f.reshape(-1)), O.fp(dxp_ref.reshape(-1)), N, Hp, Wp, C, K, R, S)
+    # device: pad (row pitch rounded to 8 elements for the forward plan), forward, backward, crop
+    pitch = (Wp * C + 7) // 8 * 8
+    dxs = eng.to_device(pkg.f32_to_bf16_bits(x))
+    canvas = eng.to_device(np.full((N, Hp, pitch), 0x4242, np.uint16))                       # pad kernel must overwrite the garbage
+    eng.pad_nhwc(dxs, canvas, N, H, W, C, pad, pad, dst_row_pitch=pitch)
+    got_canvas = canvas.to_host().reshape(N, Hp, pitch)
+    assert np.array_equal(got_canvas[:, :, :Wp * C].reshape(N, Hp, Wp, C), pkg.f32_to_bf16_bits(xp))
+    assert np.all(got_canvas[:, :, Wp * C:] == 0)
+    plan = pkg.ConvPlan(eng, N, Hp, Wp, C, K, R, S, f, None, act=0, row_pitch=pitch)
+    yd = eng.array((N, H, W, K), np.uint16)
+    plan.fwd(canvas, yd)
+    got_y = pkg.bf16_bits_to_f32(yd.to_host())
+    plan.close()
+    assert np.all(np.abs(got_y - y_ref) <= 2.0 ** -8 * np.abs(y_ref) + 1e-3)
+    dyd = eng.to_device(pkg.f32_to_bf16_bits(dy))
+    dw = eng.array((K, R, S, C))
+    eng.conv_wgrad(canvas, dyd, dw, N, Hp, Wp, C, K, R, S, row_pitch=pitch)
+    assert np.linalg.norm((dw.to_host() - dw_ref).astype(np.float64)) / np.linalg.norm(dw_ref.astype(np.float64)) <= 1e-5
+    dxp = eng.array((N, Hp, Wp, C), np.uint16)
+    eng.conv_dgrad(dyd, eng.to_device(f), dxp, N, Hp, Wp, C, K, R, S)
+    dxc = eng.array((N, H, W, C), np.uint16)
+    eng.crop_nhwc(dxp, dxc, N, H, W, C, pad, pad)
+    got_dx = pkg.bf16_bits_to_f32(dxc.to_host())
+    ref_dx = dxp_ref[:, pad:pad + H, pad:pad + W, :]
+    assert np.all(np.abs(got_dx - ref_dx) <= 2.0 ** -8 * np.abs(ref_dx) + 1e-3)
