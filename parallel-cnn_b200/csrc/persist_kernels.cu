@@ -248,26 +248,30 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
             for (int i = 0; i < MAXE; ++i) {
                 const int e = t + i * NT;
                 if (e >= cnt) break;
-                // all ranks' words are requested at once (one L2 round trip instead of `world` dependent ones: at 8 GPUs the
-                // serial version cost 2.5 us per step), then checked -- and re-polled if still stale -- in rank order
+                // Every polling round requests the words of ALL ranks still missing at once (independent loads, one L2 round
+                // trip per round) instead of waiting for rank 0, then rank 1, ...: the values of the ranks arrive within a
+                // fraction of a microsecond of each other, so after the first one is in, one more round collects the rest
+                // (measured at 4 GPUs in one session: 13.10 vs 13.29 us per step).
                 const uint2 *w0 = a.inbox + (long long)par * a.world * NPACK + e0 + e;
                 uint2 v[PCNN_MAX_PEERS];
-#pragma unroll
-                for (int q = 0; q < PCNN_MAX_PEERS; ++q)
-                    if (q < a.world) v[q] = ld_ll(w0 + (long long)q * NPACK);
-                float g = 0.0f;
+                unsigned pending = (1u << a.world) - 1u;
                 const long long t0 = clock64();
+                while (pending) {
 #pragma unroll
-                for (int q = 0; q < PCNN_MAX_PEERS; ++q) {                     // rank order: identical on all GPUs
-                    if (q < a.world) {
-                        while (v[q].y != stepid) {
-                            if (*(volatile int *)a.abort_flag) break;
-                            if (clock64() - t0 > 4 * SPIN_BUDGET) { *(volatile int *)a.abort_flag = 2; break; }
-                            v[q] = ld_ll(w0 + (long long)q * NPACK);
-                        }
-                        g += __uint_as_float(v[q].x);
+                    for (int q = 0; q < PCNN_MAX_PEERS; ++q)
+                        if ((pending >> q) & 1u) v[q] = ld_ll(w0 + (long long)q * NPACK);
+#pragma unroll
+                    for (int q = 0; q < PCNN_MAX_PEERS; ++q)
+                        if (((pending >> q) & 1u) && v[q].y == stepid) pending &= ~(1u << q);
+                    if (pending) {
+                        if (*(volatile int *)a.abort_flag) break;
+                        if (clock64() - t0 > 4 * SPIN_BUDGET) { *(volatile int *)a.abort_flag = 2; break; }
                     }
                 }
+                float g = 0.0f;
+#pragma unroll
+                for (int q = 0; q < PCNN_MAX_PEERS; ++q)                       // rank order: identical on all GPUs
+                    if (q < a.world) g += __uint_as_float(v[q].x);
                 finalize(e0 + e, g, w_mine[i]);
             }
             __syncwarp();
