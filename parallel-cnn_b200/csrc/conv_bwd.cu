@@ -28,7 +28,7 @@ bool force_fma() {
 }
 
 constexpr int WG_THREADS = 256;
-constexpr int WG_MAXO = 12;           // outputs per thread: K*R*S*C <= 3072
+constexpr int WG_MAXO = 16;           // outputs per thread: K*R*S*C <= 4096
 
 struct ConvShape {
     int N, H, W, C, K, R, S, P, Q;

@@ -6,6 +6,7 @@
 // column offset); its TMA boxes gathered 128-byte pieces of 128 different rows, and a TMA pipeline with that pattern tops
 // out at 3.6-4.4 TB/s on B200 (pcnn_measure_tma_read, mode 2) against 6.7-7.1 TB/s for contiguous boxes -- the kernel sat
 // exactly on that ceiling (4.6 TB/s, profiles/r01_README.md).  Here every TMA box is a contiguous run of one dy row:
+//   (More than 64 filters: K/64 channel groups per dy row -- K/64 x 4 boxes per stage and K/64 x 4 MMAs per row; K <= 256.)
 //   * A CTA owns a strip of <= 120 output columns and walks DOWN the rows of its share of the images.  One dy row of the
 //     strip is an A operand [128 pixels x 64 channels] (4 boxes of <= 32 pixels, one per TMEM lane quarter, overlapping by
 //     S-1 pixels so that the shift along s never crosses a warp).
@@ -30,7 +31,7 @@ using namespace pcnn_tc;
 namespace {
 
 constexpr int D2_THREADS = 192;          // warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (lane quarters)
-constexpr int D2_STAGE_BYTES = 16384;    // 4 quarters x 32 pixel rows x 128 B
+constexpr int D2_HALF_BYTES = 16384;     // one group of 64 channels: 4 quarters x 32 pixel rows x 128 B
 constexpr int D2_MAX_STAGES = 11;
 constexpr int D2_MAX_NG = 6;
 constexpr int D2_GROUP = 8;
@@ -40,6 +41,7 @@ struct Dgrad2Params {
     int n_img, H, W, P, Q;
     int nstrips, strip_w, oq, bp;        // strips per row, output columns per strip / per lane quarter, pixels per TMA box
     int ng, ring, stages;                // slot groups in flight, ring slots (8 * ng), smem stages
+    int KH;                              // channels / 64: a TMA box holds 64 channels (one 128-byte swizzle row per pixel)
     long long T;                         // n_img * H output rows in walk order
     long long dx_pitch, dx_image_rows;
     __nv_bfloat16 *dx;
@@ -51,11 +53,12 @@ struct Dgrad2Ctl {
 };
 
 // F_v[n][k] for window column n = r' * SCP + s * C + c: f[k][r' + v][s][c] (variant v drops the first v filter rows), zero padding
+// layout [variant][channel group of 64][nw][64]
 __global__ void k_dgrad2_build_variants(const float *__restrict__ f, __nv_bfloat16 *__restrict__ T, int nw, int scp, int K, int R, int S,
                                         int C) {
-    const int total = R * nw * K;
+    const int total = R * nw * K, KH = K / 64;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int k = idx % K, n = (idx / K) % nw, v = idx / (K * nw);
+        const int kl = idx % 64, n = (idx / 64) % nw, kh = (idx / (64 * nw)) % KH, v = idx / (64 * nw * KH), k = kh * 64 + kl;
         const int r = n / scp + v, j = n % scp;
         float val = 0.0f;
         if (r < R && j < S * C) val = f[(((long)k * R + r) * S + j / C) * C + j % C];
@@ -82,9 +85,10 @@ k_conv_tc_dgrad_rows(const __grid_constant__ CUtensorMap map_dy, const __grid_co
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     constexpr int BMAT = NW * 128;
-    unsigned char *bvar = base;                                         // [R][NW][64] bf16, SWIZZLE_128B
-    unsigned char *astage = base + (size_t)R * BMAT;                    // [stages][4][32][64] bf16, SWIZZLE_128B
-    Dgrad2Ctl &B = *reinterpret_cast<Dgrad2Ctl *>(astage + (size_t)p.stages * D2_STAGE_BYTES);
+    const int KH = p.KH, STAGE = KH * D2_HALF_BYTES;
+    unsigned char *bvar = base;                                         // [R][KH][NW][64] bf16, SWIZZLE_128B
+    unsigned char *astage = base + (size_t)R * KH * BMAT;               // [stages][KH][4][32][64] bf16, SWIZZLE_128B
+    Dgrad2Ctl &B = *reinterpret_cast<Dgrad2Ctl *>(astage + (size_t)p.stages * STAGE);
     const int NST = p.stages, NG = p.ng, RING = p.ring;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -106,7 +110,7 @@ k_conv_tc_dgrad_rows(const __grid_constant__ CUtensorMap map_dy, const __grid_co
         fence_barrier_init();
     }
     // pixel rows a box does not cover (box of bp < 32 pixels) must hold finite values: their TMEM lanes are never read
-    for (int i = threadIdx.x * 16; i < NST * D2_STAGE_BYTES; i += D2_THREADS * 16) *reinterpret_cast<uint4 *>(astage + i) = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x * 16; i < NST * STAGE; i += D2_THREADS * 16) *reinterpret_cast<uint4 *>(astage + i) = make_uint4(0, 0, 0, 0);
     fence_proxy_async_smem();
     if (warp == 1) tc_alloc(&B.tmem_base, 512);
     tc_fence_before();
@@ -126,8 +130,8 @@ k_conv_tc_dgrad_rows(const __grid_constant__ CUtensorMap map_dy, const __grid_co
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0 && nel > 0) {
-            bar_expect_tx(&B.bfull, (unsigned)(R * BMAT));
-            for (int v = 0; v < R; ++v) tma_load_2d(bvar + (size_t)v * BMAT, &map_b, 0, v * NW, &B.bfull);
+            bar_expect_tx(&B.bfull, (unsigned)(R * KH * BMAT));
+            for (int v = 0; v < R * KH; ++v) tma_load_2d(bvar + (size_t)v * BMAT, &map_b, 0, v * NW, &B.bfull);
             int stage = 0;
             unsigned ph = 0;
             int n = n_first, h = h_first - warm;
@@ -135,12 +139,13 @@ k_conv_tc_dgrad_rows(const __grid_constant__ CUtensorMap map_dy, const __grid_co
             for (long long i = 0; i < nrows; ++i) {
                 if (h < p.P) {
                     bar_wait_relaxed(&B.empty[stage], ph ^ 1u, 32);
-                    bar_expect_tx(&B.full[stage], (unsigned)(4 * p.bp * 128));
-                    unsigned char *a = astage + (size_t)stage * D2_STAGE_BYTES;
+                    bar_expect_tx(&B.full[stage], (unsigned)(KH * 4 * p.bp * 128));
+                    unsigned char *a = astage + (size_t)stage * STAGE;
                     const int row = n * p.P + h;
+                    for (int kh = 0; kh < KH; ++kh)
 #pragma unroll
-                    for (int g = 0; g < 4; ++g)          // pixels left of the image / right of its last dy pixel arrive as zeros
-                        tma_load_3d(a + g * 4096, &map_dy, 0, w_strip + g * p.oq - (S - 1), row, &B.full[stage]);
+                        for (int g = 0; g < 4; ++g)      // pixels left of the image / right of its last dy pixel arrive as zeros
+                            tma_load_3d(a + kh * D2_HALF_BYTES + g * 4096, &map_dy, kh * 64, w_strip + g * p.oq - (S - 1), row, &B.full[stage]);
                     if (++stage == NST) { stage = 0; ph ^= 1u; }
                 }
                 if (++h == p.H) { h = 0; ++n; }
@@ -169,11 +174,15 @@ k_conv_tc_dgrad_rows(const __grid_constant__ CUtensorMap map_dy, const __grid_co
                 if (h < p.P) {
                     bar_wait(&B.full[stage], ph);
                     tc_fence_after();
-                    const uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * (D2_STAGE_BYTES >> 4));
-                    const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(warmrow ? warm - (int)i : 0) * (BMAT >> 4));
+                    uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * ((uint32_t)STAGE >> 4));
+                    uint64_t bd = bdesc0 + (uint64_t)((uint32_t)(warmrow ? warm - (int)i : 0) * ((uint32_t)(KH * BMAT) >> 4));
                     const uint32_t dcol = tmem + (uint32_t)(pos * SCP);
+                    for (int kh = 0; kh < KH; ++kh) {          // 64 channels = 4 K steps of 16
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(dcol, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, 1u);
+                        for (int ks = 0; ks < 4; ++ks) tc_mma_bf16(dcol, ad + (uint64_t)(ks * 2), bd + (uint64_t)(ks * 2), idesc, 1u);
+                        ad += D2_HALF_BYTES >> 4;
+                        bd += BMAT >> 4;
+                    }
                     tc_commit(&B.empty[stage]);
                     if (++stage == NST) { stage = 0; ph ^= 1u; }
                 }
@@ -281,7 +290,7 @@ int launch_rows(pcnn_ctx *ctx, const CUtensorMap &map_dy, const CUtensorMap &map
 }  // namespace
 
 bool pcnn_conv_dgrad_rows_ok(int N, int H, int W, int C, int K, int R, int S, const void *dy) {
-    if (K != 64 || ((uintptr_t)dy & 15) || N <= 0 || H < R || W < S) return false;
+    if (K % 64 || K > 256 || ((uintptr_t)dy & 15) || N <= 0 || H < R || W < S) return false;
     const bool inst = (R == 3 && S == 3 && (C == 1 || C == 3 || C == 4)) || (R == 5 && S == 5 && C == 1);
     if (!inst) return false;
     const Geometry g = geometry(R, S, C);
@@ -306,13 +315,15 @@ int pcnn_conv_dgrad_rows(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f
     p.dx_pitch = row_pitch > 0 ? row_pitch : W * C;
     p.dx_image_rows = image_rows > 0 ? image_rows : H;
     p.dx = reinterpret_cast<__nv_bfloat16 *>(dx_bf16);
-    const size_t fixed = (size_t)R * g.nw * 128 + sizeof(Dgrad2Ctl) + 1024;
-    int st = (int)(((size_t)D2_SMEM_BUDGET - fixed) / D2_STAGE_BYTES);
+    p.KH = K / 64;
+    const size_t stage_bytes = (size_t)p.KH * D2_HALF_BYTES;
+    const size_t fixed = (size_t)R * p.KH * g.nw * 128 + sizeof(Dgrad2Ctl) + 1024;
+    int st = (int)(((size_t)D2_SMEM_BUDGET - fixed) / stage_bytes);
     p.stages = st > D2_MAX_STAGES ? D2_MAX_STAGES : st;
     const char *es = getenv("PCNN_DGRAD_STAGES");
     if (es && atoi(es) >= 2 && atoi(es) < p.stages) p.stages = atoi(es);
     PCNN_REQUIRE(p.stages >= 2, PCNN_ERR_ARG, "pcnn_conv_dgrad: filter variants leave no room for two stages");
-    const size_t smem = fixed + (size_t)p.stages * D2_STAGE_BYTES;
+    const size_t smem = fixed + (size_t)p.stages * stage_bytes;
 
     __nv_bfloat16 *T = nullptr;
     const size_t t_elems = (size_t)R * g.nw * K;
@@ -329,8 +340,8 @@ int pcnn_conv_dgrad_rows(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f
         if ((rc = make_map_bf16(&map_dy, const_cast<void *>(dy_bf16), 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B)))
             return rc;
-        const uint64_t bd[2] = {(uint64_t)K, (uint64_t)R * g.nw};
-        const uint64_t bs[1] = {(uint64_t)K * 2};
+        const uint64_t bd[2] = {64, (uint64_t)R * p.KH * g.nw};        // [variant][channel group][nw] rows of 64 channels
+        const uint64_t bs[1] = {128};
         const uint32_t bb[2] = {64, (uint32_t)g.nw};
         if ((rc = make_map_bf16(&map_b, T, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B))) return rc;
     }

@@ -10,6 +10,7 @@
 //   * The other operand is the Hankel matrix of the x rows, A[(rho, s, c)][pixel q] = x[p0 + rho][(q + s) * C + c] for the
 //     RB + R - 1 input rows a block of RB dy rows touches (54 of M = 64 rows at config 5); eight warps build it in shared
 //     memory from the x row segments (x is 5 % of the traffic; the 9x expansion never leaves the SM).
+//     (More than 64 filters: K/64 boxes per tile, the accumulator columns become (filter group, row, filter), K <= 256.)
 //   * D[(rho, s, c)][(row, k)] accumulates in ONE 64 x 256 TMEM accumulator for the whole kernel; the entries with
 //     rho - row = r in [0, R) are the gradient, the others are discarded.  At the end each CTA folds the RB row blocks,
 //     writes one 1,728-float partial, and a second kernel adds the partials in a fixed order (deterministic, no atomics).
@@ -35,6 +36,7 @@ constexpr int W2_DUMP_STRIDE = 257;                    // floats per accumulator
 struct Wgrad2Params {
     int n_img, H, P, Q, W, C, R, SC;
     int RB, NXR, PC, KO;                   // dy rows per tile, x rows per tile, pixels per tile, PC / 8
+    int KH;                                // filters / 64: a TMA box (and an MMA atom along N) holds 64 filters
     int nreal, nout;                       // Hankel rows in use (NXR * SC), outputs per filter (R * SC)
     int n_pb, n_ch, stages;                // row blocks per image, pixel chunks per row, smem stages
     long long x_pitch, x_image_rows;
@@ -73,7 +75,9 @@ k_conv_tc_wgrad_rows(const __grid_constant__ CUtensorMap map_dy, const Wgrad2Par
     const int C = CT > 0 ? CT : p.C;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    const int dy_bytes = p.RB * p.PC * 128;             // [RB][PC][64] bf16, SWIZZLE_128B
+    const int dy_half = p.RB * p.PC * 128;              // one box: [RB][PC][64] bf16, SWIZZLE_128B
+    const int dy_bytes = p.KH * dy_half;                // [KH filter groups][RB][PC][64]
+    const int ncols = p.KH * p.RB * 64;                 // accumulator columns (group, row, filter)
     const int hk_bytes = 64 * p.PC * 2;                 // Hankel tile [64][PC] bf16, K-major 8x8 core matrices
     const int x_bytes = p.NXR * p.xseg_stride;
     unsigned char *DY = base;
@@ -85,7 +89,7 @@ k_conv_tc_wgrad_rows(const __grid_constant__ CUtensorMap map_dy, const Wgrad2Par
     const int tiles_per_img = p.n_pb * p.n_ch;
     const int ntiles = p.n_img * tiles_per_img;
     const int SBO = p.KO * 128;                         // bytes between 8-row groups of the Hankel tile
-    const int tmem_cols = p.RB * 64 <= 32 ? 32 : (p.RB * 64 <= 64 ? 64 : (p.RB * 64 <= 128 ? 128 : 256));
+    const int tmem_cols = ncols <= 64 ? 64 : (ncols <= 128 ? 128 : 256);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NST; ++i) { bar_init(&S.full[i], 1); bar_init(&S.empty[i], 1); bar_init(&S.bready[i], W2_BUILD_WARPS); }
@@ -114,7 +118,8 @@ k_conv_tc_wgrad_rows(const __grid_constant__ CUtensorMap map_dy, const Wgrad2Par
                 if (nx > p.NXR) nx = p.NXR;
                 bar_wait_relaxed(&S.empty[stage], ph ^ 1u, 32);
                 bar_expect_tx(&S.full[stage], (unsigned)(dy_bytes + nx * xb));
-                tma_load_4d(DY + (size_t)stage * dy_bytes, &map_dy, 0, ch * p.PC, p0, n, &S.full[stage]);   // rows >= P, pixels >= Q: zeros
+                for (int kh = 0; kh < p.KH; ++kh)                                             // rows >= P, pixels >= Q: zeros
+                    tma_load_4d(DY + (size_t)stage * dy_bytes + (size_t)kh * dy_half, &map_dy, kh * 64, ch * p.PC, p0, n, &S.full[stage]);
                 if (xb > 0)
                     for (int r = 0; r < nx; ++r)
                         tma_load_1d(X + (size_t)stage * x_bytes + (size_t)r * p.xseg_stride,
@@ -126,7 +131,7 @@ k_conv_tc_wgrad_rows(const __grid_constant__ CUtensorMap map_dy, const Wgrad2Par
     } else if (warp == 1) {
         // ===== MMA issuer: D[64 x RB*64] += Hankel[64 x 16 pixels] * dy[16 pixels x RB*64]; invariant operands, constant adds =====
         if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(64, p.RB * 64, /*A K-major*/ 0, /*B MN-major*/ 1);
+            const uint32_t idesc = umma_idesc_bf16(64, ncols, /*A K-major*/ 0, /*B MN-major*/ 1);
             const uint64_t adesc0 = umma_desc_k_none(s_u32(HK), 128, (uint32_t)SBO);
             const uint64_t bdesc0 = umma_desc(s_u32(DY), (uint32_t)(p.PC * 128), 1024, 2);   // LBO = next dy row, SBO = next 8 pixels
             const uint32_t a_step = (uint32_t)hk_bytes >> 4, b_step = (uint32_t)dy_bytes >> 4;
@@ -213,7 +218,7 @@ k_conv_tc_wgrad_rows(const __grid_constant__ CUtensorMap map_dy, const Wgrad2Par
         tc_fence_after();
         const int quarter = warp & 3;                   // an M = 64 accumulator keeps row n in TMEM lane (n / 16) * 32 + n % 16
         const int n = quarter * 16 + lane;
-        for (int c0 = 0; c0 < p.RB * 64; c0 += 32) {
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
             uint32_t v[32];
             tc_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
             tc_wait_ld();
@@ -227,11 +232,12 @@ k_conv_tc_wgrad_rows(const __grid_constant__ CUtensorMap map_dy, const Wgrad2Par
     __syncthreads();
     {
         // dw[k][r][j] = sum over row blocks rb of D[(rb + r) * SC + j][rb * 64 + k]
-        float *dst = p.slots + (size_t)blockIdx.x * 64 * p.nout;
-        for (int o = threadIdx.x; o < 64 * p.nout; o += W2_THREADS) {
-            const int k = o / p.nout, rj = o % p.nout, r = rj / p.SC, j = rj % p.SC;
+        const int K = p.KH * 64;
+        float *dst = p.slots + (size_t)blockIdx.x * K * p.nout;
+        for (int o = threadIdx.x; o < K * p.nout; o += W2_THREADS) {
+            const int k = o / p.nout, rj = o % p.nout, r = rj / p.SC, j = rj % p.SC, kh = k >> 6, kl = k & 63;
             float s = 0.0f;
-            for (int rb = 0; rb < p.RB; ++rb) s += dump[((rb + r) * p.SC + j) * W2_DUMP_STRIDE + rb * 64 + k];
+            for (int rb = 0; rb < p.RB; ++rb) s += dump[((rb + r) * p.SC + j) * W2_DUMP_STRIDE + (kh * p.RB + rb) * 64 + kl];
             dst[o] = s;
         }
     }
@@ -267,20 +273,20 @@ int env_i(const char *name, int dflt) {
 // matters is that the tiles cover the [P x Q] plane with little padding (PC = 112 covers Q = 222 in two chunks: 139-147 us;
 // PC = 80 in three: 149-244 us) and that at least three stages fit; RB = 3 (139 us) ~ RB = 2 (141 us) < RB = 4 (147 us, two
 // stages).  PCNN_WGRAD_RB / PCNN_WGRAD_PC override the choice for sweeps.
-Plan plan_for(int P, int Q, int C, int R, int S) {
+Plan plan_for(int P, int Q, int C, int R, int S, int KH) {
     Plan pl;
     memset(&pl, 0, sizeof(pl));
     const int SC = S * C;
     double best = -1.0;
     for (int RB = 4; RB >= 1; --RB) {
-        if ((RB + R - 1) * SC > 64) continue;
+        if ((RB + R - 1) * SC > 64 || RB * KH * 64 > 256) continue;
         if (env_i("PCNN_WGRAD_RB", 0) > 0 && RB != env_i("PCNN_WGRAD_RB", 0)) continue;
         for (int PC = 128; PC >= 32; PC -= 16) {
             if (env_i("PCNN_WGRAD_PC", 0) > 0 && PC != env_i("PCNN_WGRAD_PC", 0)) continue;
             const int units = (((RB + R - 1) * SC + 7) / 8) * 8 * (PC / 8);
             if (units > W2_ITEMS * 32 * W2_BUILD_WARPS) continue;
             const size_t xseg = (size_t)(((PC + S) * C * 2 + 127) / 128 * 128);
-            const size_t stage = (size_t)RB * PC * 128 + (size_t)64 * PC * 2 + (size_t)(RB + R - 1) * xseg;
+            const size_t stage = (size_t)KH * RB * PC * 128 + (size_t)64 * PC * 2 + (size_t)(RB + R - 1) * xseg;
             int st = (int)(((size_t)W2_SMEM_BUDGET - sizeof(Wgrad2Ctl) - 1024) / stage);
             if (st > W2_MAX_STAGES) st = W2_MAX_STAGES;
             if (st < 2) continue;
@@ -313,20 +319,20 @@ int launch_rows(pcnn_ctx *ctx, const CUtensorMap &map_dy, const Wgrad2Params &p,
 }  // namespace
 
 bool pcnn_conv_wgrad_rows_ok(int N, int H, int W, int C, int K, int R, int S, int row_pitch, const void *x, const void *dy) {
-    if (K != 64 || ((uintptr_t)dy & 15) || ((uintptr_t)x & 15) || row_pitch % 8 || N <= 0 || H < R || W < S) return false;
-    return plan_for(H - R + 1, W - S + 1, C, R, S).ok;
+    if (K % 64 || K > 256 || ((uintptr_t)dy & 15) || ((uintptr_t)x & 15) || row_pitch % 8 || N <= 0 || H < R || W < S) return false;
+    return plan_for(H - R + 1, W - S + 1, C, R, S, K / 64).ok;
 }
 
 int pcnn_conv_wgrad_rows(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16, float *dw_f32, int N, int H, int W, int C, int K,
                          int R, int S, int row_pitch, int image_rows) {
     pcnn_device_guard g(ctx->device);
     const int P = H - R + 1, Q = W - S + 1;
-    const Plan pl = plan_for(P, Q, C, R, S);
+    const Plan pl = plan_for(P, Q, C, R, S, K / 64);
     PCNN_REQUIRE(pl.ok, PCNN_ERR_ARG, "pcnn_conv_wgrad: shape does not fit the tensor-core kernel");
     Wgrad2Params p;
     memset(&p, 0, sizeof(p));
     p.n_img = N; p.H = H; p.P = P; p.Q = Q; p.W = W; p.C = C; p.R = R; p.SC = S * C;
-    p.RB = pl.RB; p.NXR = pl.RB + R - 1; p.PC = pl.PC; p.KO = pl.PC / 8;
+    p.RB = pl.RB; p.NXR = pl.RB + R - 1; p.PC = pl.PC; p.KO = pl.PC / 8; p.KH = K / 64;
     p.nreal = p.NXR * p.SC; p.nout = R * p.SC;
     p.n_pb = (P + p.RB - 1) / p.RB; p.n_ch = (Q + p.PC - 1) / p.PC; p.stages = pl.stages;
     p.x_pitch = row_pitch > 0 ? row_pitch : W * C;

@@ -163,7 +163,9 @@ BWD_TC_SHAPES = [(1, 224, 224, 3, 64, 3, 3),      # config 5
                  (3, 37, 64, 3, 64, 3, 3),        # three pixel blocks of 28, 28, 8
                  (2, 30, 40, 1, 64, 3, 3),        # C = 1 (85 pixels per accumulator)
                  (1, 33, 32, 1, 64, 5, 5),        # 5x5 taps: lane quarters overlap by 4 rows
-                 (1, 19, 24, 4, 64, 3, 3)]        # C = 4
+                 (1, 19, 24, 4, 64, 3, 3),        # C = 4
+                 (2, 20, 40, 3, 128, 3, 3),       # 128 filters: two 64-filter groups per dy row
+                 (1, 12, 24, 1, 256, 3, 3)]       # 256 filters: four groups, one dy row per weight-gradient tile
 
 
 @pytest.mark.parametrize("shape", BWD_TC_SHAPES)
