@@ -28,7 +28,7 @@ bool force_fma() {
 }
 
 constexpr int WG_THREADS = 256;
-constexpr int WG_MAXO = 16;           // outputs per thread: K*R*S*C <= 4096
+constexpr int WG_MAXO = 20;           // outputs per thread: K*R*S*C <= 5120
 
 struct ConvShape {
     int N, H, W, C, K, R, S, P, Q;

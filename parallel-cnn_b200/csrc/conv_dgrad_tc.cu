@@ -291,7 +291,8 @@ int launch_rows(pcnn_ctx *ctx, const CUtensorMap &map_dy, const CUtensorMap &map
 
 bool pcnn_conv_dgrad_rows_ok(int N, int H, int W, int C, int K, int R, int S, const void *dy) {
     if (K % 64 || K > 256 || ((uintptr_t)dy & 15) || N <= 0 || H < R || W < S) return false;
-    const bool inst = (R == 3 && S == 3 && (C == 1 || C == 3 || C == 4)) || (R == 5 && S == 5 && C == 1);
+    const bool inst = (R == 3 && S == 3 && (C == 1 || C == 2 || C == 3 || C == 4 || C == 8)) || (R == 5 && S == 5 && (C == 1 || C == 3)) ||
+                      (R == 7 && S == 7 && C == 1);
     if (!inst) return false;
     const Geometry g = geometry(R, S, C);
     return g.ng >= 2 && g.nw <= 256 && S <= 16;
@@ -352,6 +353,10 @@ int pcnn_conv_dgrad_rows(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f
     if (R == 3 && S == 3 && C == 1) return launch_rows<3, 3, 1>(ctx, map_dy, map_b, p, grid, smem);
     if (R == 3 && S == 3 && C == 4) return launch_rows<3, 3, 4>(ctx, map_dy, map_b, p, grid, smem);
     if (R == 5 && S == 5 && C == 1) return launch_rows<5, 5, 1>(ctx, map_dy, map_b, p, grid, smem);
+    if (R == 3 && S == 3 && C == 2) return launch_rows<3, 3, 2>(ctx, map_dy, map_b, p, grid, smem);
+    if (R == 3 && S == 3 && C == 8) return launch_rows<3, 3, 8>(ctx, map_dy, map_b, p, grid, smem);
+    if (R == 5 && S == 5 && C == 3) return launch_rows<5, 5, 3>(ctx, map_dy, map_b, p, grid, smem);
+    if (R == 7 && S == 7 && C == 1) return launch_rows<7, 7, 1>(ctx, map_dy, map_b, p, grid, smem);
     pcnn_set_error("pcnn_conv_dgrad: no row-streaming instantiation for R = %d, S = %d, C = %d", R, S, C);
     return PCNN_ERR_ARG;
 }

@@ -165,7 +165,11 @@ BWD_TC_SHAPES = [(1, 224, 224, 3, 64, 3, 3),      # config 5
                  (1, 33, 32, 1, 64, 5, 5),        # 5x5 taps: lane quarters overlap by 4 rows
                  (1, 19, 24, 4, 64, 3, 3),        # C = 4
                  (2, 20, 40, 3, 128, 3, 3),       # 128 filters: two 64-filter groups per dy row
-                 (1, 12, 24, 1, 256, 3, 3)]       # 256 filters: four groups, one dy row per weight-gradient tile
+                 (1, 12, 24, 1, 256, 3, 3),       # 256 filters: four groups, one dy row per weight-gradient tile
+                 (1, 20, 40, 3, 64, 5, 5),        # 5x5x3: input gradient on the tensor cores, weight gradient falls back (75 Hankel rows)
+                 (1, 16, 24, 2, 64, 3, 3),        # C = 2
+                 (1, 12, 24, 8, 64, 3, 3),        # C = 8: weight gradient falls back
+                 (1, 20, 40, 1, 64, 7, 7)]        # 7x7 taps: lane quarters overlap by 6 pixels, 6 replayed rows
 
 
 @pytest.mark.parametrize("shape", BWD_TC_SHAPES)
