@@ -277,10 +277,10 @@ Geometry geometry(int R, int S, int C) {
 
 template <int R, int S, int C>
 int launch_rows(pcnn_ctx *ctx, const CUtensorMap &map_dy, const CUtensorMap &map_b, const Dgrad2Params &p, int grid, size_t smem) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};        // function attributes are per device
+    if (!configured[ctx->device & 63]) {
         PCNN_CUDA(cudaFuncSetAttribute(k_conv_tc_dgrad_rows<R, S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BUDGET + 2048));
-        configured = true;
+        configured[ctx->device & 63] = true;
     }
     k_conv_tc_dgrad_rows<R, S, C><<<grid, D2_THREADS, smem, ctx->stream>>>(map_dy, map_b, p);
     PCNN_CHECK_LAUNCH(ctx);

@@ -323,6 +323,13 @@ struct pcnn_conv_plan {
     CUtensorMap map_b;
 };
 
+static void free_plan(pcnn_conv_plan *plan) {
+    if (!plan) return;
+    if (plan->d_toeplitz) cudaFree(plan->d_toeplitz);
+    if (plan->d_bias) cudaFree(plan->d_bias);
+    delete plan;
+}
+
 extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int C, int K, int R, int S, int row_pitch,
                                         int image_rows, int act, const float *filt_host, const float *bias_host,
                                         pcnn_conv_plan **out) {
@@ -354,7 +361,11 @@ extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int 
     PCNN_REQUIRE(Qt > 0, PCNN_ERR_ARG,
                  "pcnn_conv_tc_plan_create: no pixel block with (Qt+S-1)*C (+ alignment remainder) <= 32, Qt*K <= 256, %%16 == 0");
     pcnn_device_guard g(ctx->device);
-    pcnn_conv_plan *pl = new pcnn_conv_plan();
+    struct PlanGuard {                       // frees a half-built plan on every early return below
+        pcnn_conv_plan *p;
+        ~PlanGuard() { free_plan(p); }
+    } guard{new pcnn_conv_plan()};
+    pcnn_conv_plan *pl = guard.p;
     pl->W = W; pl->S = S; pl->row_pitch = row_pitch;
     ConvTcParams &p = pl->p;
     p.n_img = N; p.H = image_rows; p.P = P; p.Q = Q; p.K = K; p.R = R; p.Qt = Qt; p.ncols = Qt * K; p.C = C; p.V = V; p.stages = stages;
@@ -383,12 +394,13 @@ extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int 
     }
     p.bias = pl->d_bias;
     int rc = make_map_2d(&pl->map_b, pl->d_toeplitz, TC_KCHUNK, (uint64_t)V * R * p.ncols, TC_KCHUNK * 2, TC_KCHUNK, (uint32_t)p.ncols);
-    if (rc) { delete pl; return rc; }
-    static bool configured = false;
-    if (!configured) {
+    if (rc) return rc;
+    static bool configured[64] = {};        // function attributes are per device
+    if (!configured[ctx->device & 63]) {
         PCNN_CUDA(cudaFuncSetAttribute(k_conv_tc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
-        configured = true;
+        configured[ctx->device & 63] = true;
     }
+    guard.p = nullptr;
     *out = pl;
     return PCNN_OK;
 }
@@ -398,9 +410,7 @@ extern "C" int pcnn_conv_tc_plan_destroy(pcnn_ctx *ctx, pcnn_conv_plan *plan) {
     if (!plan) return PCNN_OK;
     pcnn_device_guard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    if (plan->d_toeplitz) cudaFree(plan->d_toeplitz);
-    if (plan->d_bias) cudaFree(plan->d_bias);
-    delete plan;
+    free_plan(plan);
     return PCNN_OK;
 }
 

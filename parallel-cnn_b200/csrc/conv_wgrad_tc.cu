@@ -306,10 +306,10 @@ Plan plan_for(int P, int Q, int C, int R, int S, int KH) {
 
 template <int CT>
 int launch_rows(pcnn_ctx *ctx, const CUtensorMap &map_dy, const Wgrad2Params &p, int grid, size_t smem) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};        // function attributes are per device
+    if (!configured[ctx->device & 63]) {
         PCNN_CUDA(cudaFuncSetAttribute(k_conv_tc_wgrad_rows<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, W2_SMEM_BUDGET + 2048));
-        configured = true;
+        configured[ctx->device & 63] = true;
     }
     k_conv_tc_wgrad_rows<CT><<<grid, W2_THREADS, smem, ctx->stream>>>(map_dy, p);
     PCNN_CHECK_LAUNCH(ctx);

@@ -117,17 +117,21 @@ extern "C" int pcnn_measure_tma_read(pcnn_ctx *ctx, const void *dev_bf16, int N,
     if (p.stages > DS_MAX_STAGES) p.stages = DS_MAX_STAGES;
     const char *st = getenv("PCNN_DIAG_STAGES");
     if (st && atoi(st) > 0 && atoi(st) < p.stages) p.stages = atoi(st);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};        // function attributes are per device
+    if (!configured[ctx->device & 63]) {
         PCNN_CUDA(cudaFuncSetAttribute(k_tma_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_SMEM + 2048));
-        configured = true;
+        configured[ctx->device & 63] = true;
     }
     const size_t smem = (size_t)p.stages * p.stage_bytes + sizeof(StreamCtl) + 1024;
     unsigned *sink = nullptr;
     if ((rc = pcnn_scratch(ctx, 64, (void **)&sink))) return rc;
-    cudaEvent_t e0, e1;
-    PCNN_CUDA(cudaEventCreate(&e0));
-    PCNN_CUDA(cudaEventCreate(&e1));
+    struct Events {                          // destroyed on every return path
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } ev;
+    PCNN_CUDA(cudaEventCreate(&ev.a));
+    PCNN_CUDA(cudaEventCreate(&ev.b));
+    cudaEvent_t e0 = ev.a, e1 = ev.b;
     const int grid = p.nchunks < ctx->sm_count ? (int)p.nchunks : ctx->sm_count;
     for (int i = 0; i < 2; ++i) {
         k_tma_stream<<<grid, 64, smem, ctx->stream>>>(map, p, sink);
@@ -142,8 +146,6 @@ extern "C" int pcnn_measure_tma_read(pcnn_ctx *ctx, const void *dev_bf16, int N,
     PCNN_CUDA(cudaEventSynchronize(e1));
     float ms = 0.0f;
     PCNN_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     const double bytes = mode <= 1 ? (double)p.nchunks * p.stage_bytes : (double)pixels * 128.0;   // every byte of the tensor once
     *gbps_out = (float)(bytes * iters / (ms * 1e-3) / 1e9);
     return PCNN_OK;
@@ -197,10 +199,10 @@ extern "C" int pcnn_measure_mma_rate(pcnn_ctx *ctx, int M, int N, int a_mn_major
                      (nacc == 1 || nacc == 2 || nacc == 4 || nacc == 8) && N * nacc <= 512,
                  PCNN_ERR_ARG, "pcnn_measure_mma_rate: bad argument");
     pcnn_device_guard g(ctx->device);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};        // function attributes are per device
+    if (!configured[ctx->device & 63]) {
         PCNN_CUDA(cudaFuncSetAttribute(k_mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured = true;
+        configured[ctx->device & 63] = true;
     }
     long long *out = nullptr;
     int rc = pcnn_scratch(ctx, 64, (void **)&out);
