@@ -239,6 +239,10 @@ int pcnn_conv_wgrad(pcnn_ctx *ctx, const void *x_bf16_dev, const void *dy_bf16_d
                     int K, int R, int S, int row_pitch, int image_rows);
 int pcnn_conv_dgrad(pcnn_ctx *ctx, const void *dy_bf16_dev, const float *filt_f32_dev, void *dx_bf16_dev, int N, int H, int W,
                     int C, int K, int R, int S, int row_pitch, int image_rows);
+/* Host-only query (works without a GPU): which kernels pcnn_conv_wgrad / pcnn_conv_dgrad pick for a shape and how they tile it.
+ * out9 = { wgrad on tensor cores, dy rows per tile, pixels per tile, stages,
+ *          dgrad on tensor cores, column strips, output pixels per lane quarter, TMEM slot groups in flight, stages } */
+int pcnn_conv_bwd_plan_info(int N, int H, int W, int C, int K, int R, int S, int *out9);
 /* Zero padding for the valid-padding kernels above: pcnn_pad_nhwc_bf16 embeds dense [N][H][W][C] images into
  * a zeroed canvas [N][dst_image_rows][dst_row_pitch] at row offset pad_h, pixel offset pad_w (0 = the tight canvas
  * [H + 2 pad_h][(W + 2 pad_w) * C]); a "same" convolution is pad -> pcnn_conv_tc_fwd, its input gradient is

@@ -20,6 +20,9 @@ int pcnn_conv_dgrad_rows(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f
 bool pcnn_conv_wgrad_rows_ok(int N, int H, int W, int C, int K, int R, int S, int row_pitch, const void *x, const void *dy);
 int pcnn_conv_wgrad_rows(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16, float *dw_f32, int N, int H, int W, int C, int K,
                          int R, int S, int row_pitch, int image_rows);
+void pcnn_conv_dgrad_rows_info(int H, int W, int C, int K, int R, int S, int *out4);
+void pcnn_conv_wgrad_rows_info(int H, int W, int C, int K, int R, int S, int *out4);
+
 namespace {
 
 bool force_fma() {
@@ -235,5 +238,21 @@ extern "C" int pcnn_crop_nhwc_bf16(pcnn_ctx *ctx, const void *src_bf16, void *ds
     k_crop_nhwc<<<(int)blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const __nv_bfloat16 *>(src_bf16), reinterpret_cast<__nv_bfloat16 *>(dst_bf16),
                                                      N, H, W, C, pad_h, pad_w, src_row_pitch, src_image_rows);
     PCNN_CHECK_LAUNCH(ctx);
+    return PCNN_OK;
+}
+
+// Which kernels the backward entry points would pick for a shape and how they tile it (pure host logic, no device needed):
+// out[0] = weight gradient on the tensor cores (0/1), out[1..3] = its dy rows per tile, pixels per tile, stages;
+// out[4] = input gradient on the tensor cores (0/1), out[5..8] = its column strips, output pixels per lane quarter,
+// TMEM slot groups in flight, stages.  Pointer alignment and row pitch are assumed to qualify (16 bytes, multiple of 8).
+extern "C" int pcnn_conv_bwd_plan_info(int N, int H, int W, int C, int K, int R, int S, int *out9) {
+    PCNN_REQUIRE(out9 && N > 0 && H >= R && W >= S && C > 0 && K > 0 && R > 0 && S > 0, PCNN_ERR_ARG, "pcnn_conv_bwd_plan_info: bad argument");
+    for (int i = 0; i < 9; ++i) out9[i] = 0;
+    const void *aligned = reinterpret_cast<const void *>((uintptr_t)256);
+    if (pcnn_conv_wgrad_rows_ok(N, H, W, C, K, R, S, 8, aligned, aligned)) pcnn_conv_wgrad_rows_info(H, W, C, K, R, S, out9);
+    if (pcnn_conv_dgrad_rows_ok(N, H, W, C, K, R, S, aligned)) {
+        out9[4] = 1;
+        pcnn_conv_dgrad_rows_info(H, W, C, K, R, S, out9 + 5);
+    }
     return PCNN_OK;
 }

@@ -298,6 +298,18 @@ bool pcnn_conv_dgrad_rows_ok(int N, int H, int W, int C, int K, int R, int S, co
     return g.ng >= 2 && g.nw <= 256 && S <= 16;
 }
 
+// host-side tiling of the row-streaming input gradient, for pcnn_conv_bwd_plan_info (no GPU needed)
+void pcnn_conv_dgrad_rows_info(int H, int W, int C, int K, int R, int S, int *out4) {
+    const Geometry g = geometry(R, S, C);
+    const int oq_max = 32 - (S - 1);
+    const int nstrips = (W + 4 * oq_max - 1) / (4 * oq_max), strip_w = (W + nstrips - 1) / nstrips;
+    const size_t stage_bytes = (size_t)(K / 64) * D2_HALF_BYTES;
+    const size_t fixed = (size_t)R * (K / 64) * g.nw * 128 + sizeof(Dgrad2Ctl) + 1024;
+    int st = stage_bytes ? (int)(((size_t)D2_SMEM_BUDGET - fixed) / stage_bytes) : 0;
+    out4[0] = nstrips; out4[1] = (strip_w + 3) / 4; out4[2] = g.ng; out4[3] = st > D2_MAX_STAGES ? D2_MAX_STAGES : st;
+    (void)H;
+}
+
 int pcnn_conv_dgrad_rows(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f32_dev, void *dx_bf16, int N, int H, int W, int C, int K,
                          int R, int S, int row_pitch, int image_rows) {
     pcnn_device_guard guard(ctx->device);

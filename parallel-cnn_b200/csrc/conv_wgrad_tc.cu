@@ -323,6 +323,12 @@ bool pcnn_conv_wgrad_rows_ok(int N, int H, int W, int C, int K, int R, int S, in
     return plan_for(H - R + 1, W - S + 1, C, R, S, K / 64).ok;
 }
 
+// host-side tile choice of the weight gradient, for pcnn_conv_bwd_plan_info (no GPU needed)
+void pcnn_conv_wgrad_rows_info(int H, int W, int C, int K, int R, int S, int *out4) {
+    const Plan pl = plan_for(H - R + 1, W - S + 1, C, R, S, K / 64);
+    out4[0] = pl.ok ? 1 : 0; out4[1] = pl.RB; out4[2] = pl.PC; out4[3] = pl.stages;
+}
+
 int pcnn_conv_wgrad_rows(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16, float *dw_f32, int N, int H, int W, int C, int K,
                          int R, int S, int row_pitch, int image_rows) {
     pcnn_device_guard g(ctx->device);

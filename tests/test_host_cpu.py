@@ -162,3 +162,23 @@ def test_data_parallel_two_ranks_equal_single_process_gloo():
         g, _ = O.batch_grad(p, O.u8_to_f32(d["train_u8"][lo:hi]), d["train_labels"][lo:hi])
         p = O.apply_update(p, g.astype(np.float32), np.float32(0.1) / np.float32(hi - lo))
     np.testing.assert_allclose(res[0], p, rtol=1e-6, atol=1e-7)
+
+
+def test_conv_backward_tile_planning_is_host_logic(pkg):
+    """pcnn_conv_bwd_plan_info needs no GPU: the tile shapes DESIGN.md 3.7 quotes for BASELINE config 5, and the shapes that must
+    fall back to the FMA-pipe kernels."""
+    import ctypes as C
+
+    def info(*shape):
+        out = (C.c_int * 9)()
+        assert pkg.lib().pcnn_conv_bwd_plan_info(*shape, out) == 0
+        return list(out)
+
+    cfg5 = info(128, 224, 224, 3, 64, 3, 3)
+    assert cfg5[:4] == [1, 3, 112, 3]            # weight gradient: 3 dy rows x 112 pixels per tile (222 = 74 x 3, 2 x 112 >= 222), 3 stages
+    assert cfg5[4:8] == [1, 2, 28, 4]            # input gradient: 2 strips of 112 columns, 28 outputs per lane quarter, 4 slot groups
+    assert cfg5[8] >= 8
+    k128 = info(4, 64, 64, 3, 128, 3, 3)
+    assert k128[0] == 1 and k128[1] <= 2 and k128[4] == 1          # N = RB * 128 <= 256
+    assert info(4, 28, 28, 1, 6, 5, 5)[0] == 0 and info(4, 28, 28, 1, 6, 5, 5)[4] == 0      # LeNet c1 (6 filters): FMA-pipe kernels
+    assert info(1, 32, 32, 3, 64, 5, 5)[0] == 0 and info(1, 32, 32, 3, 64, 5, 5)[4] == 1    # 5x5x3: 75 Hankel rows > 64
