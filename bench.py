@@ -138,8 +138,9 @@ def run_reference_arm(a):
         "impl": "reference", "metric": "MNIST training images/sec", "value": value, "unit": "images/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "lenet_mnist_train_fp32", "reference_batch": 1,
-                   "note": "Sequential/Main.cpp learn() loop (batch 1 per-sample SGD is the only mode the reference has)"},
+        "config": {"workload": "lenet_mnist_train_fp32_fused_step (BASELINE.json configs[1])", "reference_batch": 1,
+                   "note": "the reference's own CPU implementation of the same workload: Sequential/Main.cpp learn() loop; "
+                           "batch-1 per-sample SGD is the only mode the reference has"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
                          "sample": f"{cores} independent single-thread replicas x {n_per_step} synthetic samples per step"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
