@@ -99,8 +99,10 @@ extern "C" int pcnn_comm_destroy(pcnn_ctx *ctx) {
         g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
     }
     ctx->nccl_comm = nullptr;
-    ctx->rank = 0;
-    ctx->world = 1;
+    if (!ctx->p2p_ready) {                 // peers still attached: the persistent kernel keeps exchanging with them
+        ctx->rank = 0;
+        ctx->world = 1;
+    }
     return PCNN_OK;
 }
 

@@ -19,8 +19,15 @@ template <typename InT> struct FusedSmem {
     float red_s1[NWARP][17];
     float dpre_f[PCNN_F];
     float f_out[PCNN_F];
+    float part[NT];                                  // persistent kernel: slot-phase partial sums of the owned chunk
     int label[2];
     alignas(8) unsigned long long mbar[3];           // [0],[1]: image stages, [2]: parameters
+    // host-streaming gate of the persistent kernel (written and read by thread 0 only)
+    const void *gate_images;
+    const unsigned *gate_ready;
+    long long gate_first, gate_chunk;
+    int *gate_abort;
+    unsigned gate_tag;
 };
 
 // ---- mbarrier / bulk-copy helpers (PTX ISA: mbarrier, cp.async.bulk) -------------------------------------
@@ -47,6 +54,31 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                      smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// ---- flag-in-data words: {fp32 value (low half), tag (high half)} in ONE naturally aligned 64-bit scalar access, which
+// the PTX memory model makes single-copy atomic.  The consumer polls the word itself until the tag matches, so neither
+// side needs a fence or a separate flag round trip (the idea of NCCL's LL protocol, applied to L2-resident buffers).
+typedef unsigned long long llword;
+__device__ __forceinline__ void ll_store(llword *p, float v, unsigned tag) {
+    asm volatile("{ .reg .b64 t; mov.b64 t, {%1, %2}; st.relaxed.gpu.global.u64 [%0], t; }" ::"l"(p), "r"(__float_as_uint(v)),
+                 "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ void ll_load(const llword *p, float &v, unsigned &tag) {
+    unsigned lo;
+    asm volatile("{ .reg .b64 t; ld.relaxed.gpu.global.u64 t, [%2]; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(tag) : "l"(p) : "memory");
+    v = __uint_as_float(lo);
+}
+// two consecutive words (16-byte aligned): two independent 64-bit accesses as far as atomicity goes
+__device__ __forceinline__ void ll_load2(const llword *p, float &v0, unsigned &tag0, float &v1, unsigned &tag1) {
+    unsigned a, b;
+    asm volatile("{ .reg .b64 t, u; ld.relaxed.gpu.global.v2.u64 {t, u}, [%4]; mov.b64 {%0, %1}, t; mov.b64 {%2, %3}, u; }"
+                 : "=r"(a), "=r"(tag0), "=r"(b), "=r"(tag1)
+                 : "l"(p)
+                 : "memory");
+    v0 = __uint_as_float(a);
+    v1 = __uint_as_float(b);
 }
 
 // 1 / (1 + e^-v) = 1 / (1 + 2^(-v log2 e)): MUFU.EX2 + MUFU.RCP.  The exponent product is rounded to fp32, so the
@@ -124,6 +156,12 @@ template <typename InT> __device__ __forceinline__ void issue_params(FusedSmem<I
     bulk_g2s(S.params, params, NPACK * 4, &S.mbar[2]);
 }
 
+// hook called by thread 0 right before it issues the bulk copy of a prefetched image (the persistent kernel gates on the
+// arrival of host-streamed chunks there); the default does nothing
+struct NoGate {
+    __device__ __forceinline__ void operator()(const void *) const {}
+};
+
 struct EvalOut {
     float *f_out;     // this image's 10 outputs or null
     uint8_t *pred;    // this image's prediction or null
@@ -134,9 +172,10 @@ struct EvalOut {
 // phase); the image must have been issued into buffer li & 1.  `next_src` (or null) is prefetched into the other buffer
 // right after the first barrier.  `params_parity` < 0: parameters already resident; otherwise wait on mbar[2] with that
 // parity before the first use of S.params (lets the parameter copy overlap the u8 -> fp32 conversion).
-template <typename InT, bool TRAIN>
+template <typename InT, bool TRAIN, typename Gate = NoGate>
 __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id, int li, const uint8_t *label_ptr,
-                                           const InT *next_src, int params_parity, Acc &A, const EvalOut &ev) {
+                                           const InT *next_src, int params_parity, Acc &A, const EvalOut &ev,
+                                           const Gate &gate = Gate()) {
     constexpr bool IS_U8 = (sizeof(InT) == 1);
     const int t = id.t, warp = id.warp, lane = id.lane;
     const int buf = li & 1;
@@ -153,7 +192,10 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
     if (t == NWK && label_ptr) S.label[buf] = (int)*label_ptr;
     if (params_parity >= 0) mbar_wait(&S.mbar[2], (unsigned)params_parity);
     __syncthreads();                                                         // sync #1
-    if (t == 0 && next_src) issue_image(S, buf ^ 1, next_src);
+    if (t == 0 && next_src) {
+        gate(next_src);
+        issue_image(S, buf ^ 1, next_src);
+    }
     // Single-lane blocks (TMA issue by lane 0 of warp 0, label fetch by lane 24 of warp 6) leave their warp diverged:
     // ptxas places the reconvergence point far downstream, and the butterfly shuffles below were then executed by
     // a partial warp (observed on B200: warp 0's FC partial sums lost lane 0).  Reconverge explicitly.
@@ -166,29 +208,32 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
 #pragma unroll
     for (int q = 0; q < PCNN_F; ++q) fcp[q] = 0.0f;
     if (id.worker) {
+        // The 8x8 input patch is walked row by row: patch row r feeds output row ox through filter row i = r - ox, so
+        // only 8 input values are live at a time (the whole patch in registers does not fit next to the accumulators).
         const float *ip = S.imgf[buf] + (4 * id.wx) * 28 + 4 * id.wy;
-        float in[8][8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
-            float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
-            in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = lo.z; in[r][3] = lo.w;
-            in[r][4] = hi.x; in[r][5] = hi.y; in[r][6] = hi.z; in[r][7] = hi.w;
-        }
         float acc[16];
 #pragma unroll
         for (int p = 0; p < 16; ++p) acc[p] = 0.0f;
         const float *wc = S.params + OFF_C1W + id.m * 25;
+        float wreg[25];
 #pragma unroll
-        for (int i = 0; i < 5; ++i)
+        for (int k = 0; k < 25; ++k) wreg[k] = wc[k];
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                const float w = wc[i * 5 + j];
+        for (int r = 0; r < 8; ++r) {
+            const float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
+            const float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
+            const float x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-                for (int ox = 0; ox < 4; ++ox)
+            for (int ox = 0; ox < 4; ++ox) {
+                const int i = r - ox;
+                if (i >= 0 && i < 5) {
 #pragma unroll
-                    for (int oy = 0; oy < 4; ++oy) acc[ox * 4 + oy] = fmaf(in[ox + i][oy + j], w, acc[ox * 4 + oy]);
+                    for (int j = 0; j < 5; ++j)
+#pragma unroll
+                        for (int oy = 0; oy < 4; ++oy) acc[ox * 4 + oy] = fmaf(x[oy + j], wreg[i * 5 + j], acc[ox * 4 + oy]);
+                }
             }
+        }
         const float bc = S.params[OFF_C1B + id.m];
         float s1pre = 0.0f;
 #pragma unroll
@@ -273,32 +318,40 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
         A.bsum_c1 += bs;                                                                    // bp_bias_c1 accumulator, layer.h:400-410
         // bp_weight_c1, layer.h:371-395 (the /576 is applied once in the epilogue)
         const float *ip = S.imgf[buf] + (4 * id.wx) * 28 + 4 * id.wy;
-        float in[8][8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
-            float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
-            in[r][0] = lo.x; in[r][1] = lo.y; in[r][2] = lo.z; in[r][3] = lo.w;
-            in[r][4] = hi.x; in[r][5] = hi.y; in[r][6] = hi.z; in[r][7] = hi.w;
-        }
+            const float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
+            const float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
+            const float x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-        for (int i = 0; i < 5; ++i)
+            for (int ox = 0; ox < 4; ++ox) {
+                const int i = r - ox;
+                if (i >= 0 && i < 5) {
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-                float s = A.dw_c1[i * 5 + j];
+                    for (int j = 0; j < 5; ++j)
 #pragma unroll
-                for (int ox = 0; ox < 4; ++ox)
-#pragma unroll
-                    for (int oy = 0; oy < 4; ++oy) s = fmaf(dpc[ox * 4 + oy], in[ox + i][oy + j], s);
-                A.dw_c1[i * 5 + j] = s;
+                        for (int oy = 0; oy < 4; ++oy) A.dw_c1[i * 5 + j] = fmaf(dpc[ox * 4 + oy], x[oy + j], A.dw_c1[i * 5 + j]);
+                }
             }
+        }
     }
 }
 
 // Reduce the register accumulators of the 216 workers in a fixed order and write this CTA's packed partial gradient
 // (slot[NPACK]).  Ends with all of the CTA's global stores issued (callers fence as needed).
-template <typename InT>
-__device__ __forceinline__ void cta_epilogue(FusedSmem<InT> &S, const ThreadId &id, const Acc &A, float *slot) {
+// plain fp32 slot (graph path) / tagged words (persistent kernel)
+struct FloatSink {
+    float *slot;
+    __device__ __forceinline__ void operator()(int p, float v) const { slot[p] = v; }
+};
+struct LLSink {
+    llword *slot;
+    unsigned tag;
+    __device__ __forceinline__ void operator()(int p, float v) const { ll_store(slot + p, v, tag); }
+};
+
+template <typename InT, typename Sink>
+__device__ __forceinline__ void cta_epilogue(FusedSmem<InT> &S, const ThreadId &id, const Acc &A, const Sink &put) {
     const int t = id.t, warp = id.warp, lane = id.lane;
     __syncthreads();
     if (id.worker) {
@@ -306,7 +359,7 @@ __device__ __forceinline__ void cta_epilogue(FusedSmem<InT> &S, const ThreadId &
         for (int i = 0; i < 25; ++i) S.red[t * RED_STRIDE + i] = A.dw_c1[i];
         S.red[t * RED_STRIDE + 25] = A.bsum_c1;
 #pragma unroll
-        for (int q = 0; q < PCNN_F; ++q) slot[OFF_FW + q * PCNN_S1 + t] = A.dw_f[q];   // column t is private to this worker
+        for (int q = 0; q < PCNN_F; ++q) put(OFF_FW + q * PCNN_S1 + t, A.dw_f[q]);   // column t is private to this worker
     }
     __syncwarp();
 #pragma unroll
@@ -332,17 +385,17 @@ __device__ __forceinline__ void cta_epilogue(FusedSmem<InT> &S, const ThreadId &
             s3 += r[(w + 3) * RED_STRIDE];
         }
         const float s = (s0 + s1) + (s2 + s3);
-        if (t < 150) slot[OFF_C1W + t] = s * (1.0f / 576.0f);
-        else slot[OFF_C1B + mm] = s;
+        if (t < 150) put(OFF_C1W + t, s * (1.0f / 576.0f));
+        else put(OFF_C1B + mm, s);
     } else if (t < 173) {                // s1 taps and s1 bias sum
         const int p = t - 156;
         float s = 0.0f;
 #pragma unroll
         for (int w = 0; w < NWARP; ++w) s += S.red_s1[w][p];
-        slot[OFF_S1W + p] = s;           // p == 16 lands on OFF_S1B
+        put(OFF_S1W + p, s);             // p == 16 lands on OFF_S1B
     }
-    if (t < PCNN_F) slot[OFF_FB + t] = A.gfb;
-    if (t == 0) slot[OFF_ERR] = A.err_acc;
+    if (t < PCNN_F) put(OFF_FB + t, A.gfb);
+    if (t == 0) put(OFF_ERR, A.err_acc);
 }
 
 // entry p of the packed vector: w += step * g in the reference's operand order (layer.h:99, :316, :412)

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_fused(const FusedArgs
         return;
     }
     if (li == 0) mbar_wait(&S.mbar[2], 0);
-    cta_epilogue(S, id, A, a.slots + (long long)blockIdx.x * NPACK);
+    cta_epilogue(S, id, A, FloatSink{a.slots + (long long)blockIdx.x * NPACK});
 }
 // ---- second kernel: fixed-order reduction of the per-CTA slots, optional update ------------------------------
 // block = 256 threads = 32 packed entries x 8 slot-phases; entry p of the packed vector is summed over slots
@@ -261,6 +261,10 @@ static int launch_advance(pcnn_ctx *ctx, const pcnn_step_src &src, int B) {
 // one full step on the context's stream: gradient kernel, slot reduction, [all-reduce + update], [cursor advance]
 static int enqueue_step(pcnn_ctx *ctx, const pcnn_step_src &src, int B) {
     int grid = 0, rc;
+    // peers attached without NCCL: only the persistent kernel can exchange the gradient; a per-step kernel chain would
+    // update every replica with its LOCAL gradient at 1/world of the step size
+    PCNN_REQUIRE(ctx->world == 1 || ctx->nccl_comm, PCNN_ERR_STATE,
+                 "single-step entry points need pcnn_comm_init_rank when world > 1 (peer attach serves pcnn_train_steps / pcnn_learn only)");
     if ((rc = pcnn_launch_fused_grad(ctx, src, B, &grid))) return rc;
     const bool distributed = ctx->world > 1 && ctx->nccl_comm;
     if ((rc = pcnn_launch_reduce(ctx, grid, B, src, !distributed, src.use_cursor && !distributed))) return rc;
@@ -338,7 +342,7 @@ extern "C" int pcnn_train_step(pcnn_ctx *ctx, long first, int B) {
 static const int GRAPH_SIZES[] = {1024, 256, 64, 16, 4, 1};
 
 static int get_step_graph(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, int nsteps, cudaGraphExec_t *out) {
-    pcnn_graph_key key{B, nsteps, ctx->world, s.pixel_type, s.rank_local ? 1 : 0, s.images, s.n};
+    pcnn_graph_key key{B, nsteps, ctx->world, s.pixel_type, s.rank_local ? 1 : 0, s.images, s.labels, s.n};
     auto it = ctx->graphs.find(key);
     if (it != ctx->graphs.end()) { *out = it->second; return PCNN_OK; }
     cudaGraph_t graph = nullptr;
@@ -440,6 +444,7 @@ static int ensure_stage(pcnn_ctx *ctx, long samples) {
     if (samples <= ctx->stage_cap_samples) return PCNN_OK;
     PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
     PCNN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    pcnn_drop_graphs(ctx);                                   // cached graphs bake the staging pointers in
     for (int i = 0; i < 2; ++i) {
         if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]);
         if (ctx->d_stage[i]) cudaFree(ctx->d_stage[i]);
@@ -476,10 +481,10 @@ extern "C" int pcnn_train_step_host(pcnn_ctx *ctx, const void *host_images, int 
     return PCNN_OK;
 }
 
-// learn() over a HOST dataset: chunks of `chunk_steps` batches are copied on the copy stream into one of two
+// Graph / NCCL mode: learn() over a HOST dataset: chunks of `chunk_steps` batches are copied on the copy stream into one of two
 // device staging buffers while the compute stream trains on the other; per-step error sums are read back.
-extern "C" int pcnn_learn_host(pcnn_ctx *ctx, const void *host_images, int pixel_type, const uint8_t *host_labels,
-                               long n, int B, int epochs, float *mean_err_out) {
+static int learn_host_chunked(pcnn_ctx *ctx, const void *host_images, int pixel_type, const uint8_t *host_labels,
+                              long n, int B, int epochs, float *mean_err_out) {
     PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_learn_host: ctx is NULL");
     PCNN_REQUIRE(host_images && host_labels && n > 0 && B > 0 && epochs > 0, PCNN_ERR_ARG, "pcnn_learn_host: bad arguments");
     PCNN_REQUIRE(pixel_type == PCNN_U8 || pixel_type == PCNN_F32, PCNN_ERR_ARG, "pcnn_learn_host: bad pixel type");
@@ -545,6 +550,146 @@ extern "C" int pcnn_learn_host(pcnn_ctx *ctx, const void *host_images, int pixel
     }
     if (mean_err_out) *mean_err_out = (float)(err / ((double)n * ctx->world));   // err is the all-reduced sum
     return PCNN_OK;
+}
+
+// Persistent mode: ONE cooperative launch per epoch.  The epoch's samples are staged in HBM chunk by chunk on the copy
+// stream (180 GB of HBM: the whole host dataset fits, up to HS_SEGMENT_BYTES per launch); every chunk is followed by a
+// 4-byte flag copy, and the kernel -- launched right after the FIRST chunk has been enqueued -- waits on the flag of a
+// sample's chunk before it issues that sample's bulk copy.  Per-step error sums go straight to mapped pinned host memory.
+// Host work per call: one launch, 2 copies per chunk, one blocking read-back at the end; no per-chunk synchronisation.
+static const size_t HS_SEGMENT_BYTES = (size_t)8 << 30;
+
+static int ensure_host_stream(pcnn_ctx *ctx, size_t image_bytes, long labels, long chunks) {
+    if (image_bytes <= ctx->hs_image_bytes && labels <= ctx->hs_label_cap && chunks <= ctx->hs_ready_cap) return PCNN_OK;
+    PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    PCNN_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    if (image_bytes > ctx->hs_image_bytes) {
+        if (ctx->d_hs_images) cudaFree(ctx->d_hs_images);
+        ctx->d_hs_images = nullptr;
+        ctx->hs_image_bytes = 0;
+        PCNN_CUDA(cudaMalloc(&ctx->d_hs_images, image_bytes));
+        ctx->hs_image_bytes = image_bytes;
+    }
+    if (labels > ctx->hs_label_cap) {
+        if (ctx->d_hs_labels) cudaFree(ctx->d_hs_labels);
+        ctx->d_hs_labels = nullptr;
+        ctx->hs_label_cap = 0;
+        PCNN_CUDA(cudaMalloc((void **)&ctx->d_hs_labels, (size_t)labels));
+        ctx->hs_label_cap = labels;
+    }
+    if (chunks > ctx->hs_ready_cap) {
+        if (ctx->d_hs_ready) cudaFree(ctx->d_hs_ready);
+        ctx->d_hs_ready = nullptr;
+        ctx->hs_ready_cap = 0;
+        const long cap = chunks < 256 ? 256 : chunks;
+        PCNN_CUDA(cudaMalloc((void **)&ctx->d_hs_ready, (size_t)cap * sizeof(unsigned)));
+        PCNN_CUDA(cudaMemset(ctx->d_hs_ready, 0, (size_t)cap * sizeof(unsigned)));
+        ctx->hs_ready_cap = cap;
+    }
+    if (!ctx->h_hs_tag) PCNN_CUDA(cudaMallocHost((void **)&ctx->h_hs_tag, sizeof(unsigned)));
+    return PCNN_OK;
+}
+
+static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel_type, const uint8_t *host_labels, long n, int B,
+                               int epochs, float *mean_err_out) {
+    const size_t px = (pixel_type == PCNN_F32 ? 4 : 1);
+    const size_t img_bytes = (size_t)PCNN_IMG * px;
+    // segment = what one launch trains on; a multiple of B so that only the last segment has a tail batch
+    long seg_samples = (long)(HS_SEGMENT_BYTES / img_bytes);
+    seg_samples = (seg_samples / B) * B;
+    if (seg_samples < B) seg_samples = B;
+    if (seg_samples > n) seg_samples = n;
+    // chunk 0: ~128 KB (at least one batch) so that the first step starts after a few microseconds of DMA; later chunks:
+    // 1/64 of the segment, between 512 KB and 16 MB (per-chunk cost: two enqueues on the host, ~2 us on the copy engine)
+    long first = (long)((128 << 10) / img_bytes);
+    first = ((first + B - 1) / B) * B;
+    if (first > seg_samples) first = seg_samples;
+    size_t cb = (size_t)seg_samples * img_bytes / 64;
+    if (cb < ((size_t)512 << 10)) cb = (size_t)512 << 10;
+    if (cb > ((size_t)16 << 20)) cb = (size_t)16 << 20;
+    long chunk = (long)(cb / img_bytes);
+    if (chunk < 1) chunk = 1;
+    const long max_chunks = 1 + (seg_samples - first + chunk - 1) / chunk;
+    int rc;
+    if ((rc = ensure_host_stream(ctx, (size_t)seg_samples * img_bytes, seg_samples, max_chunks))) return rc;
+    const long total_steps = (n + B - 1) / B;
+    if (total_steps > ctx->h_step_err_cap) {
+        PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_step_err) cudaFreeHost(ctx->h_step_err);
+        ctx->h_step_err = nullptr;
+        ctx->h_step_err_cap = 0;
+        PCNN_CUDA(cudaMallocHost((void **)&ctx->h_step_err, (size_t)total_steps * sizeof(float)));
+        ctx->h_step_err_cap = total_steps;
+    }
+    const char *hi = reinterpret_cast<const char *>(host_images);
+    const bool resident_after_first = seg_samples >= n;      // later epochs re-use the staged copy
+    double err = 0.0;
+    for (int ep = 0; ep < epochs; ++ep) {
+        long steps_done = 0;
+        for (long off = 0; off < n; off += seg_samples) {
+            const long sn = n - off < seg_samples ? n - off : seg_samples;
+            pcnn_split_binding tmp;
+            tmp.images = ctx->d_hs_images;
+            tmp.labels = ctx->d_hs_labels;
+            tmp.pixel_type = pixel_type;
+            tmp.n = sn;
+            tmp.rank_local = true;
+            const long steps = (sn + B - 1) / B;
+            const int fresh = 1 | (off == 0 ? 2 : 0);
+            if (ep > 0 && resident_after_first) {
+                if ((rc = pcnn_persist_run(ctx, tmp, B, steps, nullptr, ctx->h_step_err + steps_done, fresh))) return rc;
+            } else {
+                pcnn_persist_gate gate;
+                gate.flags = ctx->d_hs_ready;
+                gate.tag = ++ctx->hs_serial;
+                if (gate.tag == 0) gate.tag = ++ctx->hs_serial;
+                gate.first_samples = first < sn ? first : sn;
+                gate.chunk_samples = chunk;
+                *ctx->h_hs_tag = gate.tag;   // the previous user of this word has been synchronised with (end of every launch)
+                PCNN_CUDA(cudaMemcpyAsync(ctx->d_hs_labels, host_labels + off, (size_t)sn, cudaMemcpyHostToDevice, ctx->copy_stream));
+                bool launched = false;
+                long k = 0;
+                for (long co = 0; co < sn; ++k) {
+                    const long cs0 = k == 0 ? gate.first_samples : chunk;
+                    const long cs = sn - co < cs0 ? sn - co : cs0;
+                    PCNN_CUDA(cudaMemcpyAsync((char *)ctx->d_hs_images + (size_t)co * img_bytes, hi + (size_t)(off + co) * img_bytes,
+                                              (size_t)cs * img_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+                    PCNN_CUDA(cudaMemcpyAsync(ctx->d_hs_ready + k, ctx->h_hs_tag, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->copy_stream));
+                    co += cs;
+                    if (!launched) {         // the kernel starts as soon as chunk 0 is on its way
+                        if ((rc = pcnn_persist_run(ctx, tmp, B, steps, &gate, ctx->h_step_err + steps_done, fresh))) return rc;
+                        launched = true;
+                    }
+                }
+            }
+            steps_done += steps;
+            if (off + sn < n || !(ep + 1 < epochs && resident_after_first)) {
+                // the staging buffer is about to be refilled (or the call ends): wait for the kernel
+                PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+                if ((rc = pcnn_persist_check(ctx))) return rc;
+            }
+        }
+        ctx->step_err_count = steps_done;
+    }
+    PCNN_CUDA(cudaMemcpyAsync(ctx->h_scalar, ctx->d_err_total, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if ((rc = pcnn_persist_check(ctx))) return rc;
+    err = *reinterpret_cast<double *>(ctx->h_scalar);
+    if (mean_err_out) *mean_err_out = (float)(err / ((double)n * ctx->world));   // err is the all-reduced sum
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_learn_host(pcnn_ctx *ctx, const void *host_images, int pixel_type, const uint8_t *host_labels,
+                               long n, int B, int epochs, float *mean_err_out) {
+    PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_learn_host: ctx is NULL");
+    PCNN_REQUIRE(host_images && host_labels && n > 0 && B > 0 && epochs > 0, PCNN_ERR_ARG, "pcnn_learn_host: bad arguments");
+    PCNN_REQUIRE(pixel_type == PCNN_U8 || pixel_type == PCNN_F32, PCNN_ERR_ARG, "pcnn_learn_host: bad pixel type");
+    pcnn_device_guard g(ctx->device);
+    if (ctx->step_mode == PCNN_MODE_PERSISTENT)
+        PCNN_REQUIRE(use_persistent(ctx), PCNN_ERR_STATE, "persistent mode requested but peers are not attached");
+    if (use_persistent(ctx) && ctx->step_mode != PCNN_MODE_PERSISTENT_BARRIER)
+        return learn_host_streamed(ctx, host_images, pixel_type, host_labels, n, B, epochs, mean_err_out);
+    return learn_host_chunked(ctx, host_images, pixel_type, host_labels, n, B, epochs, mean_err_out);
 }
 
 // ------------------------------------------------------------------------------------------ C ABI: evaluation

@@ -111,6 +111,12 @@ extern "C" int pcnn_destroy(pcnn_ctx *ctx) {
     if (ctx->p2p_base) cudaFree(ctx->p2p_base);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->d_trace) cudaFree(ctx->d_trace);
+    if (ctx->d_hs_images) cudaFree(ctx->d_hs_images);
+    if (ctx->d_hs_labels) cudaFree(ctx->d_hs_labels);
+    if (ctx->d_hs_ready) cudaFree(ctx->d_hs_ready);
+    if (ctx->h_hs_tag) cudaFreeHost(ctx->h_hs_tag);
+    if (ctx->d_slots_ll) cudaFree(ctx->d_slots_ll);
+    if (ctx->d_params_ll) cudaFree(ctx->d_params_ll);
     if (ctx->d_bar) cudaFree(ctx->d_bar);
     if (ctx->d_abort) cudaFree(ctx->d_abort);
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
@@ -396,6 +402,7 @@ extern "C" int pcnn_dataset_bind(pcnn_ctx *ctx, int split, const void *dev_image
     PCNN_REQUIRE(((uintptr_t)dev_images & 15) == 0, PCNN_ERR_ARG, "pcnn_dataset_bind: images must be 16-byte aligned");
     pcnn_device_guard g(ctx->device);
     PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    pcnn_drop_graphs(ctx);                 // graphs captured over the old buffers must not be replayed
     release_split(ctx->split[split]);
     ctx->split[split].images = dev_images;
     ctx->split[split].labels = dev_labels;
@@ -418,6 +425,7 @@ extern "C" int pcnn_dataset_upload(pcnn_ctx *ctx, int split, const void *host_im
     PCNN_CUDA(cudaMalloc(&dl, (size_t)n + 16));
     PCNN_CUDA(cudaMemcpy(di, host_images, ib, cudaMemcpyHostToDevice));
     PCNN_CUDA(cudaMemcpy(dl, host_labels, (size_t)n, cudaMemcpyHostToDevice));
+    pcnn_drop_graphs(ctx);                 // graphs captured over the old buffers must not be replayed
     release_split(ctx->split[split]);
     ctx->split[split].images = di;
     ctx->split[split].labels = (const uint8_t *)dl;

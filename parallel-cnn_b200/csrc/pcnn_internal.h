@@ -10,7 +10,8 @@
 
 #include "../../include/pcnn.h"
 
-#define PCNN_VERSION_NUMBER 100   /* 0.1.0 */
+#define PCNN_VERSION_NUMBER 200   /* 0.2.0 */
+#define PCNN_MODE_PERSISTENT_BARRIER 3   /* internal A/B switch: the round-1 grid-barrier kernel */
 
 // Packed vectors on the device carry one extra float: the batch sum of per-sample error norms.
 constexpr int NPARAM = PCNN_NPARAM;
@@ -50,10 +51,11 @@ struct pcnn_step_src {
 struct pcnn_graph_key {
     int B, nsteps, world, pixel_type, rank_local;
     const void *images;
+    const void *labels;                     // both pointers are baked into the captured kernel arguments
     long n;
     bool operator<(const pcnn_graph_key &o) const {
-        return std::tie(B, nsteps, world, pixel_type, rank_local, images, n) <
-               std::tie(o.B, o.nsteps, o.world, o.pixel_type, o.rank_local, o.images, o.n);
+        return std::tie(B, nsteps, world, pixel_type, rank_local, images, labels, n) <
+               std::tie(o.B, o.nsteps, o.world, o.pixel_type, o.rank_local, o.images, o.labels, o.n);
     }
 };
 
@@ -86,6 +88,15 @@ struct pcnn_ctx {
     size_t stage_bytes = 0;
     long stage_cap_samples = 0;
     float *h_scalar = nullptr;              // pinned scratch for blocking scalar read-backs
+    // single-launch host streaming (pcnn_learn_host, persistent mode): the whole epoch is staged in HBM chunk by chunk
+    // while the kernel already trains on the chunks that have landed
+    void *d_hs_images = nullptr;
+    uint8_t *d_hs_labels = nullptr;
+    unsigned *d_hs_ready = nullptr;         // [hs_ready_cap] chunk flags
+    unsigned *h_hs_tag = nullptr;           // pinned source word of the flag copies
+    size_t hs_image_bytes = 0;
+    long hs_label_cap = 0, hs_ready_cap = 0;
+    unsigned hs_serial = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 
@@ -102,7 +113,10 @@ struct pcnn_ctx {
     unsigned *d_bar = nullptr;              // grid barrier counter
     int *d_abort = nullptr;                 // set by a spin loop that ran out of budget
     long long *d_trace = nullptr;           // optional phase timestamps of the persistent kernel (pcnn_persist_trace)
-    unsigned p2p_step_id = 0;               // steps issued so far (flag values of the peer exchange)
+    unsigned p2p_step_id = 0;               // distributed steps issued since pcnn_p2p_attach (tags of the peer exchange)
+    unsigned ll_step_id = 0;                // tags of the slot / parameter words (unique per context lifetime)
+    unsigned long long *d_slots_ll = nullptr;   // [MAX_SLOTS][NPACK] tagged per-CTA partial gradients
+    unsigned long long *d_params_ll = nullptr;  // [NPACK] tagged parameters
     void *p2p_base = nullptr;               // this rank's inbox + flags (IPC-exported)
     bool p2p_ready = false;
     uint2 *p2p_inbox = nullptr;             // [2][PCNN_MAX_PEERS][NPACK] words {value bits, step id}
@@ -115,6 +129,12 @@ struct pcnn_ctx {
 
     long launches = 0;
 };
+
+// destroy every cached step graph (anything a captured kernel argument depends on has changed)
+inline void pcnn_drop_graphs(pcnn_ctx *ctx) {
+    for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
+    ctx->graphs.clear();
+}
 
 // ---- error plumbing ------------------------------------------------------------------------------------
 void pcnn_set_error(const char *fmt, ...);
@@ -150,7 +170,16 @@ int pcnn_launch_reduce(pcnn_ctx *ctx, int grid_slots, int B, const pcnn_step_src
 int pcnn_launch_update(pcnn_ctx *ctx, int B, const pcnn_step_src &src, bool record_err);
 // persist_kernels.cu
 int pcnn_persist_configure(pcnn_ctx *ctx);
-int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nsteps);
+// host streaming: chunk 0 holds the first `first_samples` samples, every later chunk `chunk_samples`; the samples of
+// chunk k are readable once flags[k] == tag
+struct pcnn_persist_gate {
+    const unsigned *flags;
+    unsigned tag;
+    long long first_samples, chunk_samples;
+};
+// fresh bit 0: start at sample 0 / step 0 (no device-side counter read); bit 1: the error sum restarts at 0
+int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nsteps, const pcnn_persist_gate *gate = nullptr,
+                     float *step_err_host = nullptr, int fresh = 0);
 int pcnn_persist_check(pcnn_ctx *ctx);
 // comm.cu
 int pcnn_comm_allreduce_packed(pcnn_ctx *ctx);

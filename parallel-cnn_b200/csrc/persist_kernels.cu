@@ -42,6 +42,17 @@ struct PersistArgs {
     uint2 *inbox;             // local  [2][world][NPACK] words {value bits, step id}
     uint2 *peer_inbox[PCNN_MAX_PEERS];
     unsigned step_base;       // id of the step before the first one of this launch (ids are unique per context lifetime)
+    // flag-in-data buffers of the dataflow kernel (k_train_persist)
+    llword *slots_ll;         // [grid][NPACK] tagged partial gradients
+    llword *params_ll;        // [NPACK] tagged parameters: tag X = the parameters step X trains with
+    unsigned xstep_base;      // same for the peer exchange (advances only on distributed launches)
+    // host streaming (pcnn_learn_host): sample i may be read once ready[i / ready_chunk] == ready_tag
+    const unsigned *ready;
+    unsigned ready_tag;
+    long long ready_first;    // samples in chunk 0 (kept short so that the first step starts early)
+    long long ready_chunk;    // samples in every later chunk
+    int fresh;                // bit 0: start at sample 0 / step 0 instead of the device-side counters; bit 1: err_total = 0
+    float *step_err_host;     // optional mapped pinned array [nsteps]: per-step error sums written straight to the host
     long long *trace;         // optional [PCNN_TRACE_STEPS][6] globaltimer stamps written by CTA 0 (pcnn_persist_trace)
 };
 
@@ -101,7 +112,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target, int
 }
 
 template <typename InT>
-__global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const PersistArgs a) {
+__global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist_bar(const PersistArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem<InT> &S = *reinterpret_cast<FusedSmem<InT> *>(smem_raw);
     const ThreadId id;
@@ -155,7 +166,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         if (first) mbar_wait(&S.mbar[2], pphase & 1);   // image-less CTAs still consume this parameter phase
         ++pphase;
         PCNN_TRACE(1);
-        cta_epilogue(S, id, A, a.slots + (long long)c * NPACK);
+        cta_epilogue(S, id, A, FloatSink{a.slots + (long long)c * NPACK});
         PCNN_TRACE(2);
 
         // position of the next step; its first image is prefetched across the barriers
@@ -297,14 +308,343 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
     }
 }
 
+
+// =====================================================================================================================
+// k_train_persist -- the dataflow version: no grid barrier, no fence on the critical path.
+//
+// Every buffer that crosses CTAs holds tagged 64-bit words {fp32 value, step id} (fused_body.cuh: ll_store / ll_load);
+// a consumer polls the words it needs until they carry the id it expects.  Per step X every CTA
+//   1. copies the tagged parameters (tag X) from L2 into shared memory,
+//   2. runs forward + backward over its images,
+//   3. reduces its register accumulators and writes its tagged partial gradient (slot, tag X),
+//   4. as OWNER of a chunk of the packed vector: gathers that chunk from all slots (tag X), adds them in slot order,
+//      [N > 1: exchanges the chunk with the peer GPUs, rank order], updates its parameters -- which it keeps in
+//      registers for the whole launch -- and publishes them with tag X + 1.
+// Two L2 round trips per step instead of two fenced grid barriers.  Buffer reuse needs no extra synchronisation: a CTA
+// can only overwrite its slot (step X + 1) after it has fetched ALL parameters tagged X + 1, i.e. after every owner has
+// finished reading the slots of step X; an owner can only overwrite its parameters (tag X + 2) after it has read all
+// slots of step X + 1, i.e. after every CTA has fetched the parameters tagged X + 1.
+// Determinism: slot order, phase order and rank order are fixed -> bit-identical reruns and replicas.
+// =====================================================================================================================
+// phase boundaries of one step as seen by CTA 0: 0 step start, 1 parameters resident, 2 images done, 3 slot published,
+// 4 owned chunk reduced (and exchanged), 5 parameters published
+constexpr long long POLL_BUDGET = 4000000000LL;   // cycles a single wait may take before the launch is aborted
+
+struct PollGuard {
+    long long t0;
+    unsigned n;
+    int *abort_flag;
+    __device__ __forceinline__ explicit PollGuard(int *f) {
+        t0 = clock64();
+        n = 0;
+        abort_flag = f;
+    }
+    // true: give up (somebody aborted or this wait ran out of budget)
+    __device__ __forceinline__ bool expired(int code) {
+        if ((++n & 1023u) != 0) return false;
+        if (*(volatile int *)abort_flag) return true;
+        if (clock64() - t0 > POLL_BUDGET) { *(volatile int *)abort_flag = code; return true; }
+        return false;
+    }
+};
+
+// all threads: tagged parameters -> S.params (ordered before the readers by the next block barrier)
+template <typename InT>
+__device__ __forceinline__ void fetch_params_ll(FusedSmem<InT> &S, const llword *pll, unsigned tag, int *abort_flag) {
+    constexpr int NPAIR = NPACK / 2;                          // 1172 16-byte pairs
+    constexpr int ROUNDS = (NPAIR + NT - 1) / NT;             // 6
+    static_assert(NPACK % 2 == 0, "pairs");
+    const int t = threadIdx.x;
+    float2 *dst = reinterpret_cast<float2 *>(S.params);
+    PollGuard guard(abort_flag);
+    {   // stage 1: poll ONE pair per thread until the owners have published (keeps the idle polling traffic at 1/6)
+        float v0, v1;
+        unsigned g0, g1;
+        for (;;) {
+            ll_load2(pll + 2 * t, v0, g0, v1, g1);
+            if (g0 == tag && g1 == tag) break;
+            if (guard.expired(1)) break;
+        }
+        dst[t] = make_float2(v0, v1);
+    }
+    // stage 2: the remaining pairs, all loads in flight at once; stragglers are re-polled
+    float v0[ROUNDS - 1], v1[ROUNDS - 1];
+    unsigned pend = 0;
+#pragma unroll
+    for (int j = 1; j < ROUNDS; ++j)
+        if (t + j * NT < NPAIR) pend |= 1u << j;
+    while (pend) {
+        unsigned g0[ROUNDS - 1], g1[ROUNDS - 1];
+#pragma unroll
+        for (int j = 1; j < ROUNDS; ++j)
+            if ((pend >> j) & 1u) ll_load2(pll + 2 * (t + j * NT), v0[j - 1], g0[j - 1], v1[j - 1], g1[j - 1]);
+#pragma unroll
+        for (int j = 1; j < ROUNDS; ++j)
+            if (((pend >> j) & 1u) && g0[j - 1] == tag && g1[j - 1] == tag) {
+                dst[t + j * NT] = make_float2(v0[j - 1], v1[j - 1]);
+                pend &= ~(1u << j);
+            }
+        if (pend && guard.expired(1)) break;
+    }
+}
+
+// thread 0: wait until the host-streamed chunk holding `src` has landed (pcnn_learn_host), then make the DMA-written
+// bytes visible to the async proxy that the bulk copy reads through.  The gate's constants live in shared memory.
+template <typename InT> struct ChunkGate {
+    FusedSmem<InT> *S;
+    __device__ __forceinline__ void operator()(const void *src) const {
+        const unsigned *ready = S->gate_ready;
+        if (!ready) return;
+        const long long sample = (reinterpret_cast<const InT *>(src) - reinterpret_cast<const InT *>(S->gate_images)) / PCNN_IMG;
+        const long long first = S->gate_first;
+        const unsigned *f = ready + (sample < first ? 0 : 1 + (sample - first) / S->gate_chunk);
+        const unsigned want = S->gate_tag;
+        PollGuard guard(S->gate_abort);
+        while (*(const volatile unsigned *)f != want)
+            if (guard.expired(3)) break;
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+    }
+};
+
+// Steps 2 and 3 of a step: forward + backward over this CTA's images b = c, c + G, ... < nb, then the CTA reduction into
+// the tagged slot.  Deliberately NOT inlined: the register allocation of the image pass (accumulators + patch rows, right
+// at the 128-register budget of 2 CTAs/SM) then does not compete with the persistent loop's own state.  Returns the
+// advanced CTA-local image counter.
+template <typename InT>
+__device__ __noinline__ int step_images(FusedSmem<InT> *Sp, const InT *img_base, const uint8_t *lab_base, int c, int G, int nb,
+                                        int li, llword *slot, unsigned tag, long long *trace_row) {
+    FusedSmem<InT> &S = *Sp;
+    const ThreadId id;
+    const ChunkGate<InT> gate{Sp};
+    Acc A;
+    A.zero();
+    const EvalOut ev = {nullptr, nullptr, true};
+    for (int b = c; b < nb; b += G, ++li) {
+        const int bn = b + G;
+        image_pass<InT, true>(S, id, li, lab_base + b, bn < nb ? img_base + (long long)bn * PCNN_IMG : nullptr, -1, A, ev, gate);
+    }
+    if (trace_row && id.t == 0) trace_row[2] = globaltimer_ns();
+    cta_epilogue(S, id, A, LLSink{slot, tag});
+    return li;
+}
+
+template <typename InT>
+__global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const PersistArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem<InT> &S = *reinterpret_cast<FusedSmem<InT> *>(smem_raw);
+    const ThreadId id;
+    const int t = id.t;
+    const int G = gridDim.x, c = blockIdx.x;
+    const InT *images = reinterpret_cast<const InT *>(a.images);
+    const ChunkGate<InT> gate{&S};
+    if (t == 0) {
+        S.gate_images = a.images;
+        S.gate_ready = a.ready;
+        S.gate_chunk = a.ready_chunk;
+        S.gate_first = a.ready_first;
+        S.gate_abort = a.abort_flag;
+        S.gate_tag = a.ready_tag;
+    }
+
+    // owner geometry: this CTA owns packed entries [e0, e0 + cnt); thread t owns entries e0 + t + i * NT
+    const int chunk = (NPACK + G - 1) / G;
+    const int e0 = c * chunk;
+    const int cnt = e0 >= NPACK ? 0 : (e0 + chunk > NPACK ? NPACK - e0 : chunk);
+    const int PH = chunk >= NT ? 1 : NT / chunk;         // slot phases when the chunk is narrower than the CTA
+    constexpr int MAXE = (NPACK + NT - 1) / NT;          // entries a thread can own (G == 1)
+    constexpr int KB = 12;                               // slot words one thread keeps in flight
+
+    long long cursor = (a.fresh & 1) ? 0 : *a.cursor;
+    const int step_idx0 = (a.fresh & 1) ? 0 : *a.step_idx;
+    const long long stride = a.rank_local ? (long long)a.B : (long long)a.B * a.world;
+    auto shard = [&](long long cur, long long &base, int &nb) {
+        base = cur + (a.rank_local ? 0 : (long long)a.rank * a.B);
+        const long long avail = a.n_total - base;
+        nb = avail <= 0 ? 0 : (avail < a.B ? (int)avail : a.B);
+    };
+    long long base;
+    int nb;
+    shard(cursor, base, nb);
+
+    init_barriers(S);
+    int li = 0;                 // CTA-local running image counter (staging buffer + mbarrier phase)
+    if (t == 0 && c < nb) {
+        const InT *src = images + (base + c) * PCNN_IMG;
+        gate(src);
+        issue_image(S, 0, src);
+    }
+    __syncwarp();   // lane 0 rejoins its warp (see image_pass)
+
+    // launch prologue: owners read their parameters once (they live in registers from here on) and publish them for
+    // the first step
+    float w0 = 0.0f;            // chunk < NT (the usual case): the one parameter this thread owns
+#pragma unroll 1
+    for (int e = t; e < cnt; e += NT) {
+        const int p = e0 + e;
+        const float w = p < NPARAM ? __ldcg(a.params + p) : 0.0f;
+        if (e == t) w0 = w;
+        ll_store(a.params_ll + p, w, a.step_base + 1u);
+    }
+
+    for (int s = 0; s < a.nsteps; ++s) {
+        const unsigned tag = a.step_base + (unsigned)s + 1u;
+        PCNN_TRACE(0);
+        // ---- 1. this step's parameters: L2 -> shared memory (the first block barrier of the image pass orders them)
+        fetch_params_ll(S, a.params_ll, tag, a.abort_flag);
+        PCNN_TRACE(1);
+
+        // ---- 2. forward + backward over this CTA's images, 3. CTA reduction -> tagged slot
+        li = step_images<InT>(&S, images + base * PCNN_IMG, a.labels + base, c, G, nb, li, a.slots_ll + (long long)c * NPACK, tag,
+                              (a.trace && c == 0 && s < PCNN_TRACE_STEPS) ? a.trace + s * 6 : nullptr);
+        PCNN_TRACE(3);
+
+        // position of the next step; its first image is prefetched while the gradient is being reduced
+        long long ncur = cursor + stride;
+        if (ncur >= a.n_total) ncur = 0;
+        long long nbase;
+        int nnb;
+        shard(ncur, nbase, nnb);
+        const bool more = s + 1 < a.nsteps;
+        if (t == 0 && more && c < nnb) {
+            const InT *src = images + (nbase + c) * PCNN_IMG;
+            gate(src);
+            issue_image(S, li & 1, src);
+        }
+        __syncwarp();
+
+        // ---- 4. owner: gather my chunk from all slots in slot order; 5. [N > 1: exchange with the peer GPUs], update,
+        //         publish the next step's parameters
+        const float step = a.dt / (float)effective_global_batch(cursor, true, a.n_total, a.B, a.world, a.rank_local);
+        const unsigned xtag = a.xstep_base + (unsigned)s + 1u;
+        // entry p: local sum g, parameter value before the step w_old; returns the updated parameter
+        auto finalize = [&](int p, float g, float w_old) -> float {
+            if (a.world > 1) {
+                // "low-latency" push: every 8-byte inbox word carries {value, step id}; one NVLink one-way latency per step.
+                // Every polling round then requests the words of ALL ranks still missing at once; the ranks' values are
+                // added in rank order, so all GPUs compute bit-identical sums.
+                const int par = (int)(xtag & 1u);
+                for (int q = 0; q < a.world; ++q)
+                    st_ll(a.peer_inbox[q] + ((long long)par * a.world + a.rank) * NPACK + p, g, xtag);
+                const uint2 *w0p = a.inbox + (long long)par * a.world * NPACK + p;
+                uint2 v[PCNN_MAX_PEERS];
+                unsigned pending = (1u << a.world) - 1u;
+                PollGuard guard(a.abort_flag);
+                while (pending) {
+#pragma unroll
+                    for (int q = 0; q < PCNN_MAX_PEERS; ++q)
+                        if ((pending >> q) & 1u) v[q] = ld_ll(w0p + (long long)q * NPACK);
+#pragma unroll
+                    for (int q = 0; q < PCNN_MAX_PEERS; ++q)
+                        if (((pending >> q) & 1u) && v[q].y == xtag) pending &= ~(1u << q);
+                    if (pending && guard.expired(2)) break;
+                }
+                g = 0.0f;
+#pragma unroll
+                for (int q = 0; q < PCNN_MAX_PEERS; ++q)
+                    if (q < a.world) g += __uint_as_float(v[q].x);
+            }
+            a.grads[p] = g;
+            float w = 0.0f;
+            if (p < NPARAM) {
+                w = updated_entry(w_old, p, g, step);
+                a.params[p] = w;
+            } else {
+                *a.err_total = (s == 0 && (a.fresh & 2)) ? (double)g : *a.err_total + (double)g;
+                a.step_err[(step_idx0 + s) & (STEP_ERR_CAP - 1)] = g;
+                if (a.step_err_host) a.step_err_host[s] = g;
+            }
+            ll_store(a.params_ll + p, w, tag + 1u);
+            return w;
+        };
+        if (chunk < NT) {
+            const int e = t % chunk, ph = t / chunk;
+            float sum = 0.0f;
+            if (e < cnt && ph < PH) {
+                const llword *sp = a.slots_ll + e0 + e;
+                PollGuard guard(a.abort_flag);
+                {   // wait for my first word before requesting the rest (bounds the idle polling traffic)
+                    float v;
+                    unsigned g;
+                    for (;;) {
+                        ll_load(sp + (long long)ph * NPACK, v, g);
+                        if (g == tag || guard.expired(1)) break;
+                    }
+                }
+                for (int k0 = ph; k0 < G; k0 += KB * PH) {
+                    float v[KB];
+                    unsigned pend = 0;
+#pragma unroll
+                    for (int u = 0; u < KB; ++u) {
+                        v[u] = 0.0f;
+                        if (k0 + u * PH < G) pend |= 1u << u;
+                    }
+                    while (pend) {
+                        unsigned g[KB];
+#pragma unroll
+                        for (int u = 0; u < KB; ++u)
+                            if ((pend >> u) & 1u) ll_load(sp + (long long)(k0 + u * PH) * NPACK, v[u], g[u]);
+#pragma unroll
+                        for (int u = 0; u < KB; ++u)
+                            if (((pend >> u) & 1u) && g[u] == tag) pend &= ~(1u << u);
+                        if (pend && guard.expired(1)) break;
+                    }
+#pragma unroll
+                    for (int u = 0; u < KB; ++u) sum += v[u];                  // slot order within the phase
+                }
+            }
+            if (ph < PH) S.part[ph * chunk + e] = sum;
+            __syncthreads();
+            PCNN_TRACE(4);
+            if (t < cnt) {
+                float g = S.part[t];
+                for (int q = 1; q < PH; ++q) g += S.part[q * chunk + t];       // phase order
+                w0 = finalize(e0 + t, g, w0);
+            }
+        } else {                                                               // G <= 10: a thread owns several entries
+            PCNN_TRACE(4);
+#pragma unroll 1
+            for (int e = t; e < cnt; e += NT) {
+                const int p = e0 + e;
+                const llword *sp = a.slots_ll + p;
+                PollGuard guard(a.abort_flag);
+                float acc = 0.0f;
+                for (int k = 0; k < G; ++k) {
+                    float v;
+                    unsigned g;
+                    for (;;) {
+                        ll_load(sp + (long long)k * NPACK, v, g);
+                        if (g == tag || guard.expired(1)) break;
+                    }
+                    acc += v;
+                }
+                // the parameter is re-read: this thread itself stored it one step earlier
+                finalize(p, acc, p < NPARAM ? __ldcg(a.params + p) : 0.0f);
+            }
+        }
+        __syncwarp();
+        PCNN_TRACE(5);
+        cursor = ncur;
+        base = nbase;
+        nb = nnb;
+    }
+    if (c == 0 && t == 0) {
+        *a.cursor = cursor;
+        *a.step_idx = step_idx0 + a.nsteps;
+    }
+}
+
 template <typename InT> int persist_cap(int *out) {
-    int per_sm = 0;
+    int per_sm = 0, per_sm_bar = 0;
     cudaError_t e = cudaFuncSetAttribute(k_train_persist<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)sizeof(FusedSmem<InT>));
     if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_train_persist_bar<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<InT>));
+    if (e == cudaSuccess)
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_train_persist<InT>, NT, sizeof(FusedSmem<InT>));
+    if (e == cudaSuccess)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_bar, k_train_persist_bar<InT>, NT, sizeof(FusedSmem<InT>));
     if (e != cudaSuccess) return pcnn_fail_cuda(e, "persistent kernel occupancy", __FILE__, __LINE__);
-    *out = per_sm;
+    *out = per_sm < per_sm_bar ? per_sm : per_sm_bar;
     return PCNN_OK;
 }
 
@@ -318,15 +658,30 @@ int pcnn_persist_configure(pcnn_ctx *ctx) {
     if (per_sm > FUSED_CTAS_PER_SM) per_sm = FUSED_CTAS_PER_SM;
     ctx->persist_cap = per_sm * ctx->sm_count;
     if (ctx->persist_cap > MAX_SLOTS) ctx->persist_cap = MAX_SLOTS;
+    PCNN_CUDA(cudaMalloc((void **)&ctx->d_slots_ll, (size_t)MAX_SLOTS * NPACK * sizeof(llword)));
+    PCNN_CUDA(cudaMalloc((void **)&ctx->d_params_ll, (size_t)NPACK * sizeof(llword)));
+    PCNN_CUDA(cudaMemset(ctx->d_slots_ll, 0, (size_t)MAX_SLOTS * NPACK * sizeof(llword)));
+    PCNN_CUDA(cudaMemset(ctx->d_params_ll, 0, (size_t)NPACK * sizeof(llword)));
     return PCNN_OK;
 }
 
-// nsteps cursor-driven steps of batch B over split `s` in one cooperative launch
-int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nsteps) {
+// nsteps cursor-driven steps of batch B over split `s` in one cooperative launch.  `gate` (optional) makes the kernel wait
+// for host-streamed chunks; `step_err_host` (optional, mapped pinned) receives every step's error sum.
+int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nsteps, const pcnn_persist_gate *gate,
+                     float *step_err_host, int fresh) {
     PCNN_REQUIRE(ctx->persist_cap > 0, PCNN_ERR_STATE, "persistent kernel cannot be co-resident on this device");
     PCNN_REQUIRE(ctx->world == 1 || ctx->p2p_ready, PCNN_ERR_STATE, "persistent multi-GPU steps need pcnn_p2p_attach");
+    const bool barrier_variant = ctx->step_mode == PCNN_MODE_PERSISTENT_BARRIER;
     while (nsteps > 0) {
         const int k = nsteps > 1000000 ? 1000000 : (int)nsteps;   // keeps the 32-bit barrier counter in range
+        // tags are unique per context lifetime; long before the 32-bit ids wrap, start over on cleared buffers
+        if (ctx->ll_step_id > 0xF0000000u) {
+            PCNN_CUDA(cudaMemsetAsync(ctx->d_slots_ll, 0, (size_t)MAX_SLOTS * NPACK * sizeof(llword), ctx->stream));
+            PCNN_CUDA(cudaMemsetAsync(ctx->d_params_ll, 0, (size_t)NPACK * sizeof(llword), ctx->stream));
+            ctx->ll_step_id = 0;
+        }
+        PCNN_REQUIRE(ctx->world == 1 || ctx->p2p_step_id <= 0xF0000000u, PCNN_ERR_STATE,
+                     "peer-exchange step ids exhausted: pcnn_p2p_detach and attach again on all ranks");
         PersistArgs a{};
         a.images = s.images;
         a.labels = s.labels;
@@ -347,20 +702,37 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
         a.rank_local = s.rank_local ? 1 : 0;
         a.dt = ctx->lr;
         a.inbox = ctx->p2p_inbox;
-        for (int q = 0; q < PCNN_MAX_PEERS; ++q) {
-            a.peer_inbox[q] = ctx->p2p_peer_inbox[q];
-        }
+        for (int q = 0; q < PCNN_MAX_PEERS; ++q) a.peer_inbox[q] = ctx->p2p_peer_inbox[q];
         a.trace = ctx->d_trace;
-        a.step_base = ctx->p2p_step_id;
-        ctx->p2p_step_id += (unsigned)k;
+        a.slots_ll = ctx->d_slots_ll;
+        a.params_ll = ctx->d_params_ll;
+        a.step_base = barrier_variant ? ctx->p2p_step_id : ctx->ll_step_id;
+        a.xstep_base = ctx->p2p_step_id;
+        // k + 1 ids per launch: the parameters published after the last step (tag base + k + 1) must never look like the
+        // first step's parameters of the next launch (pcnn_set_params may have changed them in between)
+        ctx->ll_step_id += (unsigned)k + 1u;
+        if (ctx->world > 1) ctx->p2p_step_id += (unsigned)k;      // identical on all ranks: same launches after attach
+        if (gate) {
+            a.ready = gate->flags;
+            a.ready_tag = gate->tag;
+            a.ready_first = gate->first_samples;
+            a.ready_chunk = gate->chunk_samples;
+        }
+        a.fresh = fresh;
+        fresh = 0;                                                 // a split longer than one launch continues
+        a.step_err_host = step_err_host;
+        if (step_err_host) step_err_host += k;
         int grid = B < ctx->persist_cap ? B : ctx->persist_cap;
-        PCNN_CUDA(cudaMemsetAsync(ctx->d_bar, 0, sizeof(unsigned), ctx->stream));
         void *args[] = {&a};
-        cudaError_t e;
-        if (s.pixel_type == PCNN_U8)
-            e = cudaLaunchCooperativeKernel((void *)k_train_persist<uint8_t>, dim3(grid), dim3(NT), args, sizeof(FusedSmem<uint8_t>), ctx->stream);
-        else
-            e = cudaLaunchCooperativeKernel((void *)k_train_persist<float>, dim3(grid), dim3(NT), args, sizeof(FusedSmem<float>), ctx->stream);
+        const void *fn;
+        if (barrier_variant) {
+            PCNN_CUDA(cudaMemsetAsync(ctx->d_bar, 0, sizeof(unsigned), ctx->stream));
+            fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist_bar<uint8_t> : (const void *)k_train_persist_bar<float>;
+        } else {
+            fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist<uint8_t> : (const void *)k_train_persist<float>;
+        }
+        const size_t smem = s.pixel_type == PCNN_U8 ? sizeof(FusedSmem<uint8_t>) : sizeof(FusedSmem<float>);
+        cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), args, smem, ctx->stream);
         if (e != cudaSuccess) return pcnn_fail_cuda(e, "cudaLaunchCooperativeKernel(k_train_persist)", __FILE__, __LINE__);
         ctx->launches += 1;
         ctx->persist_used = true;
@@ -377,7 +749,7 @@ int pcnn_persist_check(pcnn_ctx *ctx) {
     if (flag) {
         cudaMemset(ctx->d_abort, 0, sizeof(int));
         pcnn_set_error("persistent training kernel aborted: %s wait exceeded its cycle budget",
-                       flag == 2 ? "peer-GPU exchange" : "grid barrier");
+                       flag == 2 ? "peer-GPU exchange" : (flag == 3 ? "host-streamed chunk" : "slot / parameter"));
         return PCNN_ERR_STATE;
     }
     return PCNN_OK;
@@ -423,6 +795,11 @@ extern "C" int pcnn_p2p_attach(pcnn_ctx *ctx, const void *handles, int rank, int
         ctx->p2p_peer_inbox[q] = reinterpret_cast<uint2 *>(base);
     }
     ctx->p2p_inbox = ctx->p2p_peer_inbox[rank];
+    // exchange ids restart at every attach: all ranks then issue the same distributed launches and agree on them; the
+    // caller must barrier between attach and the first distributed step (a peer may still be clearing its inbox)
+    PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    PCNN_CUDA(cudaMemset(ctx->p2p_base, 0, p2p_layout::inbox_bytes()));
+    ctx->p2p_step_id = 0;
     ctx->rank = rank;
     ctx->world = world;
     ctx->p2p_ready = true;
@@ -465,7 +842,7 @@ extern "C" int pcnn_persist_trace(pcnn_ctx *ctx, long long *host_out, int cap_st
 
 extern "C" int pcnn_set_step_mode(pcnn_ctx *ctx, int mode) {
     PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_set_step_mode: ctx is NULL");
-    PCNN_REQUIRE(mode >= PCNN_MODE_AUTO && mode <= PCNN_MODE_PERSISTENT, PCNN_ERR_ARG, "pcnn_set_step_mode: bad mode %d", mode);
+    PCNN_REQUIRE(mode >= PCNN_MODE_AUTO && mode <= PCNN_MODE_PERSISTENT_BARRIER, PCNN_ERR_ARG, "pcnn_set_step_mode: bad mode %d", mode);
     ctx->step_mode = mode;
     return PCNN_OK;
 }

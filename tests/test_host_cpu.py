@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol(pkg):
     assert len(names) >= 60
     for n in names:
         assert hasattr(L, n), f"libpcnn.so does not export {n} declared in include/pcnn.h"
-    assert L.pcnn_version() == 100
+    assert L.pcnn_version() == 200
 
 
 def test_sass_is_sm100a_only(pkg):
