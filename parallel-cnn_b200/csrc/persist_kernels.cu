@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
 
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned tag = a.step_base + (unsigned)s + 1u;
+        if ((s & 63) == 63 && *(volatile int *)a.abort_flag) break;            // somebody gave up: leave quickly
         PCNN_TRACE(0);
         // ---- 1. this step's parameters: L2 -> shared memory (the first block barrier of the image pass orders them)
         fetch_params_ll(S, a.params_ll, tag, a.abort_flag);
