@@ -89,19 +89,76 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(kernel, batch, steps):
+    """DRAM bytes of one launch from profiles/traffic.json ({kernel: {batch: bytes_per_step}}), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return float(d[kernel][str(batch)]["dram_bytes_per_step"]) * steps
+    except Exception:
+        return None
+
+
 def synthetic(n, seed):
     rng = np.random.default_rng(seed)
     return rng.integers(0, 256, (n, 784), dtype=np.uint8), rng.integers(0, 10, n, dtype=np.uint8)
 
 
+MNIST_DIR = os.path.join(ROOT, "oracle", "_ref", "data")
+
+
+def load_training_set(copies=5):
+    """The real MNIST training split (the four IDX files staged by oracle/Makefile next to the compiled reference) through
+    the engine's own loader, concatenated `copies` times so that the device-resident set (235 MB) is larger than the
+    126 MB L2 -- every step then reads its batch from HBM.  Falls back to synthetic MNIST-shaped bytes when the files
+    are absent.  Returns (images u8 [n,784], labels u8 [n], description)."""
+    img, lab = os.path.join(MNIST_DIR, "train-images.idx3-ubyte"), os.path.join(MNIST_DIR, "train-labels.idx1-ubyte")
+    if os.path.exists(img) and os.path.exists(lab):
+        import pcnn_loader
+        rc, images, labels = pcnn_loader.load().mnist_load_u8(img, lab)
+        if rc == 0:
+            return (np.ascontiguousarray(np.tile(images, (copies, 1))), np.ascontiguousarray(np.tile(labels, copies)),
+                    f"mnist (train split, 60000 images x {copies} concatenated copies = {copies * 47.04:.0f} MB)")
+    imgs, labs = synthetic(DATASET_IMAGES, 7)
+    return imgs, labs, "synthetic"
+
+
+def host_cores():
+    """CPUs this process may actually use: scheduler affinity, capped by the cgroup CPU quota (a 1-GPU lease can report
+    128 CPUs and grant a dozen).  Returns (count, sorted affinity list, description)."""
+    aff = sorted(os.sched_getaffinity(0))
+    n, why = len(aff), f"affinity {len(aff)} of {os.cpu_count()}"
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                quota, period = txt[0], float(txt[1])
+            else:
+                quota, period = txt[0], float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota not in ("max", "-1"):
+                q = max(1, int(float(quota) / period))
+                if q < n:
+                    n, why = q, why + f", cgroup quota {float(quota) / period:.1f} CPUs"
+            break
+        except Exception:
+            continue
+    return n, aff, why
+
+
 # ----------------------------------------------------------------------------------------------- reference arm
 def _ref_worker(args):
-    """One host core: the unmodified reference (or the oracle port) trains on `n` synthetic samples per step."""
-    wid, n, steps, warmup = args
+    """One host core (pinned): the unmodified reference (or the oracle port) trains on `n` samples per step."""
+    wid, cpu, n, steps, warmup, native = args
+    if cpu is not None:
+        try:
+            os.sched_setaffinity(0, {cpu})
+        except Exception:
+            pass
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
-    imgs, labs = synthetic(n, 1000 + wid)
-    ref = O.reference()
+    imgs, labs, _ = load_training_set(copies=1)
+    lo = (wid * n) % max(1, imgs.shape[0] - n)
+    imgs, labs = np.ascontiguousarray(imgs[lo:lo + n]), np.ascontiguousarray(labs[lo:lo + n])
+    ref = O.reference(native=native)
     secs = np.zeros(1, np.float64)
     if ref is not None:
         run = lambda: ref.ref_learn_loop_u8(O.u8p(imgs.reshape(-1)), O.u8p(labs), n, O.dp(secs))
@@ -116,10 +173,11 @@ def _ref_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_reference_throughput(cores, n_per_step, steps, warmup):
+def cpu_reference_throughput(cores, cpu_list, n_per_step, steps, warmup, native=False):
     import multiprocessing as mp
+    jobs = [(w, cpu_list[w % len(cpu_list)] if cpu_list else None, n_per_step, steps, warmup, native) for w in range(cores)]
     with mp.get_context("fork").Pool(cores) as pool:
-        times = pool.map(_ref_worker, [(w, n_per_step, steps, warmup) for w in range(cores)])
+        times = pool.map(_ref_worker, jobs)
     return cores * steps * n_per_step / max(times), max(times)
 
 
@@ -130,19 +188,21 @@ def run_reference_arm(a):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     kind = "reference" if O.reference() is not None else "port"
-    cores = os.cpu_count() or 1
+    cores, aff, why = host_cores()
+    _, _, data = load_training_set(copies=1)
     # bounded sample: ~60 s of CPU work in total at ~4.4 k img/s/core
     n_per_step = int(max(8, min(4096, 60.0 * 4400 / max(1, a.steps + a.warmup))))
-    value, secs = cpu_reference_throughput(cores, n_per_step, a.steps, a.warmup)
+    value, secs = cpu_reference_throughput(cores, aff, n_per_step, a.steps, a.warmup)
     line = {
         "impl": "reference", "metric": "MNIST training images/sec", "value": value, "unit": "images/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * secs / a.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": data,
         "config": {"workload": "lenet_mnist_train_fp32_fused_step (BASELINE.json configs[1])", "reference_batch": 1,
                    "note": "the reference's own CPU implementation of the same workload: Sequential/Main.cpp learn() loop; "
                            "batch-1 per-sample SGD is the only mode the reference has"},
-        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
-                         "sample": f"{cores} independent single-thread replicas x {n_per_step} synthetic samples per step"},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind, "cores_how": why,
+                         "sample": f"{cores} independent single-thread replicas (one per granted CPU, pinned with "
+                                   f"sched_setaffinity) x {n_per_step} samples per step, g++ -O2"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -194,6 +254,25 @@ def conv_roofline(eng, pkg, stream, hbm_peak, peak_src, n_img=128, iters=10):
             "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src, "l2": "846 MB per pass, larger than L2"}
 
 
+def reference_cuda_baseline(samples=20000):
+    """The reference's own GPU path (CUDA/main.cu + layer.cu, unmodified, built for sm_100a by oracle/Makefile) timed on
+    this B200 with a device synchronise around learn() -- batch 1, ~38 driver calls per image.  Baseline
+    only: it is numerically wrong in two kernels and is never used as a checker."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "cuda_ref_bench")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe, str(samples)], cwd=os.path.join(ROOT, "oracle", "_ref"), capture_output=True, text=True, timeout=300)
+        for ln in r.stdout.splitlines():
+            if ln.startswith("REF_CUDA"):
+                kv = dict(x.split("=") for x in ln.split()[1:])
+                return {"value": float(kv["images_per_s"]), "unit": "images/s", "samples": int(kv["samples"]),
+                        "seconds": float(kv["seconds"]), "kind": "reference CUDA/ (unmodified, sm_100a, batch 1, device-synchronised wall clock)"}
+        return {"unavailable": (r.stderr or r.stdout)[-200:]}
+    except Exception as exc:
+        return {"unavailable": str(exc)[:200]}
+
+
 def run_ours(a):
     import torch
     import pcnn_loader
@@ -216,8 +295,10 @@ def run_ours(a):
     eng = pkg.Engine(local, stream.cuda_stream)
     B, K, W = a.batch, a.steps, max(a.warmup, 3)
 
-    # synthetic MNIST-shaped dataset, identical on every rank (ranks read disjoint windows of it)
-    imgs, labs = synthetic(DATASET_IMAGES, 7)
+    # the training set (real MNIST x5 when staged, else synthetic bytes), identical on every rank: ranks read disjoint
+    # windows of every global batch
+    imgs, labs, data_desc = load_training_set()
+    n_data = imgs.shape[0]
     eng.dataset_upload(pkg.TRAIN_SET, imgs, labs)
     if world > 1:
         if a.mode == "graph":        # per-step kernels in CUDA graphs + one ncclAllReduce of the packed gradient per step
@@ -244,11 +325,67 @@ def run_ours(a):
                 eng.comm_init_rank(uid[0], rank, world)
                 a.mode = "graph"
     eng.set_step_mode({"auto": pkg.MODE_AUTO, "graph": pkg.MODE_GRAPH, "persistent": pkg.MODE_PERSISTENT}[a.mode])
+    if a.persist_tune:
+        eng.persist_tune(a.persist_tune)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed_steps(batch, k, w):
+        """w warm-up + k timed cursor-driven steps of `batch` images per GPU; returns ms (max over ranks)."""
+        eng.train_steps_prepare(batch, k)
+        eng.train_steps(0, batch, w)
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        eng.train_steps(-1, batch, k)
+        a1.record(stream)
+        barrier()
+        t_ms = a0.elapsed_time(a1)
+        if world > 1:
+            tt = torch.tensor([t_ms], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_ms = float(tt.item())
+        return t_ms
+
+    # ---- multi-GPU parity, where the driver sees it (SURVEY.md 8a x4): 4 data-parallel steps of 1024 images per GPU
+    # against the same global batch on ONE GPU (a second, unattached engine on rank 0); replicas must be bit-identical
+    parity = None
+    if world > 1:
+        PB, PK = 1024, 4
+        p0 = pkg.init_params_reference()
+        eng.set_params(p0)
+        barrier()
+        eng.train_steps(0, PB, PK)
+        eng.sync()
+        p_dp = eng.get_params()
+        bits = torch.from_numpy(p_dp.view(np.int32).copy()).cuda()
+        lo, hi = bits.clone(), bits.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        identical = bool(torch.equal(lo, hi))
+        rel = 0.0
+        if rank == 0:
+            n_sub = PB * world * PK
+            with pkg.Engine(local) as solo:
+                solo.dataset_upload(pkg.TRAIN_SET, imgs[:n_sub], labs[:n_sub])
+                solo.set_params(p0)
+                solo.train_steps(0, PB * world, PK)
+                solo.sync()
+                p_1 = solo.get_params()
+            rel = float(np.linalg.norm(p_dp.astype(np.float64) - p_1) / np.linalg.norm(p_1.astype(np.float64)))
+        parity = {"rel_l2_params": rel, "replicas_bit_identical": identical, "global_batch": PB * world, "steps": PK,
+                  "bound": 1e-6, "against": "one GPU training the same global batch (second engine on rank 0)"}
+        ok = torch.tensor([1 if (identical and rel <= 1e-6) else 0], device="cuda")
+        dist.broadcast(ok, src=0)
+        if int(ok.item()) == 0:
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU parity failed", "parity": parity}), flush=True)
+            raise SystemExit(3)
+        eng.set_params(p0)
+        barrier()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -278,7 +415,7 @@ def run_ours(a):
     n_e2e = K2 * B
     hi = torch.empty((n_e2e, 784), dtype=torch.uint8, pin_memory=True)
     hl = torch.empty((n_e2e,), dtype=torch.uint8, pin_memory=True)
-    sel = (np.arange(n_e2e) + rank * n_e2e) % DATASET_IMAGES        # every rank streams its own shard
+    sel = (np.arange(n_e2e) + rank * n_e2e) % n_data                # every rank streams its own shard
     hi.numpy()[:] = imgs[sel]
     hl.numpy()[:] = labs[sel]
     eng.learn_host(hi.numpy(), hl.numpy(), B=B, epochs=1)            # warm-up pass (graphs, staging buffers)
@@ -294,6 +431,18 @@ def run_ours(a):
         e2e_s = float(t.item())
     e2e_val = n_e2e * world / e2e_s
     barrier()
+
+    # ---- BASELINE.json configs[3]: 1024 images per GPU (weak) and a fixed global batch of 8192 (strong)
+    b1024 = None
+    if not a.no_batch1024:
+        K4 = max(50, min(K, 1000))
+        ms_w = timed_steps(1024, K4, 20)
+        bs = 8192 // world
+        ms_s = ms_w if bs == 1024 else timed_steps(bs, K4, 20)
+        b1024 = {"weak_1024_per_gpu": {"value": K4 * 1024 * world / (ms_w * 1e-3), "ms_per_step": ms_w / K4, "global_batch": 1024 * world},
+                 "strong_global_8192": {"value": K4 * 8192 / (ms_s * 1e-3), "ms_per_step": ms_s / K4, "batch_per_gpu": bs},
+                 "steps": K4, "unit": "images/s",
+                 "parity_note": "batches beyond the oracle's reach are covered by additivity / determinism tests (tests/test_fused_gpu.py)"}
 
     # ---- roofline of the dominant kernel + live fp32 peak
     line = None
@@ -318,10 +467,9 @@ def run_ours(a):
         roof = {"bound": "fp32_fma" if frac_f >= frac_h else "hbm",
                 "achieved": tf if frac_f >= frac_h else gbs, "peak": fp32_peak if frac_f >= frac_h else hbm_peak,
                 "unit": "TFLOP/s" if frac_f >= frac_h else "GB/s", "frac": max(frac_f, frac_h),
-                # dram__bytes_read.sum + dram__bytes_write.sum of the kernel from the committed `ncu --set full` captures
-                # (profiles/r01_persist_b256_ncu_full_subset.csv: 52.23 MB per 256-step launch at B = 256;
-                #  profiles/r01_fused_b256_ncu_full_subset.csv: 249.9 KB per k_fused launch), scaled to this launch
-                "traffic": (launch_steps * 204035.0 if persistent else 249900.0) if B == 256 else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel per step, read from the summary that
+                # scripts/ncu_traffic.py wrote from the round's `ncu --set full` capture (null when no capture matches)
+                "traffic": measured_traffic("k_train_persist" if persistent else "k_fused", B, launch_steps),
                 "kernel": kernel, "kernel_ms": launch_ms,
                 "fp32": {"achieved": tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": frac_f,
                          "peak_source": "measured live (pcnn_measure_fp32_peak FFMA micro-benchmark)"},
@@ -331,32 +479,38 @@ def run_ours(a):
                                        "tflops": B * FLOPS_PER_IMAGE / (k_ms * 1e-3) / 1e12}}
         # ---- CPU baseline beside it (N = 1 only): the unmodified reference on ONE host core
         cpu = None
+        ref_gpu = None
         if world == 1 and not a.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "tests"))
             import oracle_lib as O
             kind = "reference" if O.reference() is not None else "port"
             n_cpu = 40000
-            v, secs = cpu_reference_throughput(1, n_cpu, 1, 0)
+            ncores, aff, why = host_cores()
+            v, secs = cpu_reference_throughput(1, aff[:1], n_cpu, 1, 0)
             cpu = {"value": v, "unit": "images/s", "cores": 1, "kind": kind,
-                   "sample": f"{n_cpu} synthetic samples, Sequential/Main.cpp learn() loop (batch 1), {secs:.1f} s",
-                   "host_cores_available": os.cpu_count()}
+                   "sample": f"{n_cpu} MNIST samples, Sequential/Main.cpp learn() loop (batch 1), g++ -O2, {secs:.1f} s",
+                   "host_cores_granted": ncores, "host_cores_how": why}
+            if O.reference(native=True) is not None:      # best single-core build of the same sources
+                v3, s3 = cpu_reference_throughput(1, aff[:1], n_cpu, 1, 0, native=True)
+                cpu["native_O3"] = {"value": v3, "flags": "-O3 -march=x86-64-v3 (FMA contraction: timing only)", "seconds": s3}
+            ref_gpu = reference_cuda_baseline()
         conv = None
         if world == 1 and not a.no_conv:
             conv = conv_roofline(eng, pkg, stream, hbm_peak, peak_src)
         line = {
             "metric": "MNIST training images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "fp32", "data": data_desc,
             "config": {"workload": "lenet_mnist_train_fp32_fused_step (BASELINE.json configs[1])", "batch_per_gpu": B,
                        "global_batch": B * world, "pixel_type": "u8", "parallelism": f"dp{world}",
                        "step_mode": ("graph+nccl" if world > 1 else "graph") if a.mode == "graph" else
                                     ("persistent+nvlink_p2p" if world > 1 else "persistent"),
-                       "l2": f"inputs larger than L2: steps walk a {DATASET_IMAGES}-image ({DATASET_IMAGES * 784 / 1e6:.0f} MB) device-resident set",
+                       "l2": f"inputs larger than L2: steps walk a {n_data}-image ({n_data * 784 / 1e6:.0f} MB) device-resident set",
                        "update": "w += (dt / global_batch) * sum_b g_b, dt = 0.1 (equals the reference at batch 1)"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * 785 * world,
                     "d2h_bytes_per_step": 4 * world, "steps": K2, "api": "Engine.learn_host (pcnn_learn_host), pinned host u8"},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-            "conv": conv,
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "ref_gpu_baseline": ref_gpu, "clocks": clocks,
+            "parity": parity, "batch1024": b1024, "conv": conv,
         }
         print(json.dumps(line), flush=True)
     eng.close()
@@ -374,6 +528,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-conv", action="store_true", help="skip the conv fwd+bwd roofline block (N = 1 only)")
+    ap.add_argument("--persist-tune", type=int, default=0, help="pcnn_persist_tune knob (profiling runs: 2 = clusters without the cooperative attribute)")
+    ap.add_argument("--no-batch1024", action="store_true", help="skip the 1024-per-GPU / global-8192 block")
     ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent"],
                     help="auto/persistent: one cooperative kernel runs all K steps (N > 1: in-kernel NVLink exchange); "
                          "graph: per-step kernels replayed from CUDA graphs (N > 1: ncclAllReduce per step)")

@@ -200,14 +200,25 @@ int pcnn_p2p_export(pcnn_ctx *ctx, void *handle_out, size_t *handle_bytes);
 int pcnn_p2p_attach(pcnn_ctx *ctx, const void *handles, int rank, int world);
 int pcnn_p2p_detach(pcnn_ctx *ctx);
 /* How cursor-driven steps (pcnn_train_steps, pcnn_learn, pcnn_learn_host) execute: PCNN_MODE_PERSISTENT = one
- * cooperative kernel running all steps (grid barriers, in-kernel reduction/update/exchange); PCNN_MODE_GRAPH = CUDA
- * graphs of per-step kernels (+ NCCL all-reduce when distributed); PCNN_MODE_AUTO (default) = persistent whenever it
- * can serve the configuration (single GPU, or peers attached), else graph. */
+ * cooperative kernel running all steps (thread-block clusters + tagged words through L2 instead of grid barriers,
+ * in-kernel reduction/update/exchange); PCNN_MODE_GRAPH = CUDA graphs of per-step kernels (+ NCCL all-reduce when
+ * distributed); PCNN_MODE_AUTO (default) = persistent whenever it can serve the configuration (single GPU, or peers
+ * attached), else graph. */
 int pcnn_set_step_mode(pcnn_ctx *ctx, int mode);
-/* Phase timestamps of the persistent kernel (ns; 6 per step: step start, images done, slot published, barrier 1, chunk
- * reduced/exchanged/updated, barrier 2; first 256 steps of a launch, CTA 0).  host_out == NULL arms tracing for the
+/* Geometry of the most recent persistent launch and what the device can hold: out6 = { grid, cluster size, co-resident CTAs,
+ * co-resident CTAs when launched as clusters, the cluster size the kernel is built for, 1 if the launches are cooperative }.
+ * pcnn_persist_tune(ctx, 1) forces the variant without clusters (0 = automatic), 2 keeps the clusters but launches without
+ * the cooperative attribute (profilers that re-issue cooperative launches drop the cluster dimension) -- measurement knobs
+ * for the runs under profiles/. */
+int pcnn_persist_info(pcnn_ctx *ctx, int *out6);
+int pcnn_persist_tune(pcnn_ctx *ctx, int max_cluster);
+/* Phase timestamps of the persistent kernel (ns; 6 per step: step start, parameters resident, images done, cluster slot
+ * written, owned chunk gathered, parameters published; first 256 steps of a launch, CTA 0).  host_out == NULL arms tracing for the
  * following launches, host_out != NULL reads the stamps back. */
 int pcnn_persist_trace(pcnn_ctx *ctx, long long *host_out, int cap_steps);
+/* the same six stamps of EVERY CTA at step 128 of the traced launch, rows of 8 (six stamps, SM id, spare): their spread is
+ * the skew between CTAs that the gradient owners have to wait for */
+int pcnn_persist_trace_ctas(pcnn_ctx *ctx, long long *host_out, int cap_ctas);
 
 /* ------------------------------------------------------------------ north_star extension ops (parity unpinned by the reference)
  * max-pool k x k stride k over [C][H][W] planes with argmax cache (flat index i*k+j, first maximum wins) */

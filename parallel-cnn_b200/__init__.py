@@ -9,7 +9,7 @@ The directory name contains a hyphen, so import it through ``pcnn_loader.load()`
 it as the module ``parallel_cnn_b200``).
 """
 from ._lib import (  # noqa: F401
-    LIB_PATH, NPARAM, OFF, PcnnError, U8, F32, TRAIN_SET, TEST_SET, MODE_AUTO, MODE_GRAPH, MODE_PERSISTENT, MODE_PERSISTENT_BARRIER,
+    LIB_PATH, NPARAM, OFF, PcnnError, U8, F32, TRAIN_SET, TEST_SET, MODE_AUTO, MODE_GRAPH, MODE_PERSISTENT,
     lib, declared_symbols, init_params_reference, mnist_load_u8,
 )
 from .engine import ConvPlan, DeviceArray, Engine, bf16_bits_to_f32, f32_to_bf16_bits  # noqa: F401

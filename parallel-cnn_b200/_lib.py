@@ -14,7 +14,6 @@ NPARAM = 2343
 OFF = dict(c1w=(0, 150), c1b=(150, 156), s1w=(156, 172), s1b=(172, 173), fw=(173, 2333), fb=(2333, 2343))
 U8, F32 = 0, 1
 MODE_AUTO, MODE_GRAPH, MODE_PERSISTENT = 0, 1, 2
-MODE_PERSISTENT_BARRIER = 3   # internal A/B switch (round-1 grid-barrier kernel); not part of include/pcnn.h
 TRAIN_SET, TEST_SET = 0, 1
 
 
@@ -101,6 +100,9 @@ _SIG = {
     "pcnn_p2p_detach": [_vp],
     "pcnn_set_step_mode": [_vp, _i],
     "pcnn_persist_trace": [_vp, _vp, _i],
+    "pcnn_persist_trace_ctas": [_vp, _vp, _i],
+    "pcnn_persist_info": [_vp, _vp],
+    "pcnn_persist_tune": [_vp, _i],
     "pcnn_maxpool_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
     "pcnn_maxpool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
     "pcnn_softmax_ce": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp],

@@ -20,14 +20,18 @@ template <typename InT> struct FusedSmem {
     float dpre_f[PCNN_F];
     float f_out[PCNN_F];
     float part[NT];                                  // persistent kernel: slot-phase partial sums of the owned chunk
+    alignas(16) float recv[NPACK + 16];              // persistent kernel: [cluster rank][my share] gradient pieces pushed by the peers
+    float lut[256];                                  // u8 pixel -> fp32 (mnist.h:145 + Main.cpp:64), filled once per kernel
     int label[2];
-    alignas(8) unsigned long long mbar[3];           // [0],[1]: image stages, [2]: parameters
+    alignas(8) unsigned long long mbar[5];           // [0],[1]: image stages, [2]: parameters (bulk copy or peer pushes),
+                                                     // [3]: gradient pieces pushed by the cluster peers
     // host-streaming gate of the persistent kernel (written and read by thread 0 only)
     const void *gate_images;
     const unsigned *gate_ready;
     long long gate_first, gate_chunk;
     int *gate_abort;
     unsigned gate_tag;
+    int aborted;                                     // persistent kernel: a wait of this CTA has given up; later waits return at once
 };
 
 // ---- mbarrier / bulk-copy helpers (PTX ISA: mbarrier, cp.async.bulk) -------------------------------------
@@ -81,6 +85,51 @@ __device__ __forceinline__ void ll_load2(const llword *p, float &v0, unsigned &t
     v1 = __uint_as_float(b);
 }
 
+// ---- thread-block clusters: ranks, the hardware cluster barrier, distributed shared memory ----------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_idx() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r));
+    return r;
+}
+// all threads of all CTAs of the cluster; release/acquire also orders the distributed-shared-memory accesses around it
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(const void *own_smem, unsigned rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(own_smem)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void dsmem_st_f2(uint32_t addr, float x, float y) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+// asynchronous store into (any) CTA of the cluster that signals the destination CTA's mbarrier with its byte count: the
+// receiver needs no barrier and no fence, it waits on its own mbarrier like for a bulk copy
+__device__ __forceinline__ void dsmem_st_async_f32(uint32_t addr, float v, uint32_t mbar_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(addr), "f"(v), "r"(mbar_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void dsmem_st_async_f2(uint32_t addr, float x, float y, uint32_t mbar_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(addr), "f"(x), "f"(y),
+                 "r"(mbar_addr)
+                 : "memory");
+}
+__device__ __forceinline__ float dsmem_ld_f(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 // 1 / (1 + e^-v) = 1 / (1 + 2^(-v log2 e)): MUFU.EX2 + MUFU.RCP.  The exponent product is rounded to fp32, so the
 // relative error of e^-v grows like |v| * 6e-8 (|v| < 30 here); the sigmoid inherits at most (1 - sigma) of it.
 __device__ __forceinline__ float sigmoid_fast(float v) {
@@ -98,9 +147,6 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// mnist.h:145 + Main.cpp:64: (float)((double)u / 255.0).  u / 255 has a period-8 binary expansion, so rounding the
-// exact quotient straight to fp32 equals rounding via double (checked for all 256 values in tests/).
-__device__ __forceinline__ float pixel_to_float(uint8_t u) { return __fdiv_rn((float)u, 255.0f); }
 
 struct ThreadId {
     int t, warp, lane, m, wx, wy;
@@ -138,8 +184,13 @@ template <typename InT> __device__ __forceinline__ void init_barriers(FusedSmem<
         mbar_init(&S.mbar[0], 1);
         mbar_init(&S.mbar[1], 1);
         mbar_init(&S.mbar[2], 1);
+        mbar_init(&S.mbar[3], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // mnist.h:145 + Main.cpp:64: (float)((double)u / 255.0).  u / 255 has a period-8 binary expansion, so rounding the exact
+    // quotient straight to fp32 equals rounding via double (checked for all 256 values in tests/); one table per CTA instead
+    // of four IEEE divisions per thread and image
+    for (int u = threadIdx.x; u < 256; u += NT) S.lut[u] = __fdiv_rn((float)u, 255.0f);
     __syncthreads();
 }
 
@@ -172,24 +223,34 @@ struct EvalOut {
 // phase); the image must have been issued into buffer li & 1.  `next_src` (or null) is prefetched into the other buffer
 // right after the first barrier.  `params_parity` < 0: parameters already resident; otherwise wait on mbar[2] with that
 // parity before the first use of S.params (lets the parameter copy overlap the u8 -> fp32 conversion).
-template <typename InT, bool TRAIN, typename Gate = NoGate>
-__device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id, int li, const uint8_t *label_ptr,
-                                           const InT *next_src, int params_parity, Acc &A, const EvalOut &ev,
-                                           const Gate &gate = Gate()) {
+// P0 of an image: wait until it has landed in staging buffer li & 1, convert it to fp32 (u8 path), fetch the label.  No
+// barrier: the caller's next block barrier (sync #1 of image_pass) publishes the results.
+template <typename InT>
+__device__ __forceinline__ void image_prepare(FusedSmem<InT> &S, const ThreadId &id, int li, const uint8_t *label_ptr) {
     constexpr bool IS_U8 = (sizeof(InT) == 1);
-    const int t = id.t, warp = id.warp, lane = id.lane;
+    const int t = id.t;
     const int buf = li & 1;
-    const unsigned parity = (li >> 1) & 1;
-    // ---- P0: the image has landed; convert to fp32 (u8 path), fetch the label
-    mbar_wait(&S.mbar[buf], parity);
+    mbar_wait(&S.mbar[buf], (unsigned)(li >> 1) & 1u);
     if (IS_U8) {
         if (t < 196) {
             uchar4 q = reinterpret_cast<const uchar4 *>(S.stage[buf])[t];
-            float4 f = make_float4(pixel_to_float(q.x), pixel_to_float(q.y), pixel_to_float(q.z), pixel_to_float(q.w));
+            float4 f = make_float4(S.lut[q.x], S.lut[q.y], S.lut[q.z], S.lut[q.w]);
             reinterpret_cast<float4 *>(S.imgf[buf])[t] = f;
         }
     }
     if (t == NWK && label_ptr) S.label[buf] = (int)*label_ptr;
+}
+
+// `prepared`: image_prepare has already run for this image (the persistent kernel does it while it waits for the step's
+// parameters).
+template <typename InT, bool TRAIN, typename Gate = NoGate>
+__device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id, int li, const uint8_t *label_ptr,
+                                           const InT *next_src, int params_parity, Acc &A, const EvalOut &ev,
+                                           const Gate &gate = Gate(), bool prepared = false) {
+    const int t = id.t, warp = id.warp, lane = id.lane;
+    const int buf = li & 1;
+    // ---- P0: the image has landed; convert to fp32 (u8 path), fetch the label
+    if (!prepared) image_prepare(S, id, li, label_ptr);
     if (params_parity >= 0) mbar_wait(&S.mbar[2], (unsigned)params_parity);
     __syncthreads();                                                         // sync #1
     if (t == 0 && next_src) {
@@ -205,33 +266,32 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
     float o[16];         // this worker's 4x4 block of c1 outputs
     float s1o = 0.0f;    // its s1 output
     float fcp[PCNN_F];
+    float fw[PCNN_F];    // this worker's column of f.weight, used again by the backward chain
 #pragma unroll
-    for (int q = 0; q < PCNN_F; ++q) fcp[q] = 0.0f;
+    for (int q = 0; q < PCNN_F; ++q) fcp[q] = fw[q] = 0.0f;
     if (id.worker) {
-        // The 8x8 input patch is walked row by row: patch row r feeds output row ox through filter row i = r - ox, so
-        // only 8 input values are live at a time (the whole patch in registers does not fit next to the accumulators).
+        // Filter row i outermost: its five weights and one 8-wide patch row are all that is live next to the 16
+        // accumulators (the whole 8x8 patch or all 25 weights in registers do not fit beside the gradient accumulators).
+        // Every accumulator still receives its 25 terms in (i, j) order.
         const float *ip = S.imgf[buf] + (4 * id.wx) * 28 + 4 * id.wy;
         float acc[16];
 #pragma unroll
         for (int p = 0; p < 16; ++p) acc[p] = 0.0f;
         const float *wc = S.params + OFF_C1W + id.m * 25;
-        float wreg[25];
 #pragma unroll
-        for (int k = 0; k < 25; ++k) wreg[k] = wc[k];
+        for (int i = 0; i < 5; ++i) {
+            float w[5];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
-            const float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
-            const float x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+            for (int j = 0; j < 5; ++j) w[j] = wc[i * 5 + j];
 #pragma unroll
             for (int ox = 0; ox < 4; ++ox) {
-                const int i = r - ox;
-                if (i >= 0 && i < 5) {
+                const float4 lo = *reinterpret_cast<const float4 *>(ip + (ox + i) * 28);
+                const float4 hi = *reinterpret_cast<const float4 *>(ip + (ox + i) * 28 + 4);
+                const float x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-                    for (int j = 0; j < 5; ++j)
+                for (int j = 0; j < 5; ++j)
 #pragma unroll
-                        for (int oy = 0; oy < 4; ++oy) acc[ox * 4 + oy] = fmaf(x[oy + j], wreg[i * 5 + j], acc[ox * 4 + oy]);
-                }
+                    for (int oy = 0; oy < 4; ++oy) acc[ox * 4 + oy] = fmaf(x[oy + j], w[j], acc[ox * 4 + oy]);
             }
         }
         const float bc = S.params[OFF_C1B + id.m];
@@ -244,7 +304,10 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
         s1o = sigmoid_fast(s1pre + S.params[OFF_S1B]);
         // fp_preact_f partial products (layer.h:184-203): this worker owns input k = t
 #pragma unroll
-        for (int q = 0; q < PCNN_F; ++q) fcp[q] = S.params[OFF_FW + q * PCNN_S1 + t] * s1o;
+        for (int q = 0; q < PCNN_F; ++q) {
+            fw[q] = S.params[OFF_FW + q * PCNN_S1 + t];
+            fcp[q] = fw[q] * s1o;
+        }
     } else {
 #pragma unroll
         for (int p = 0; p < 16; ++p) o[p] = 0.0f;
@@ -258,29 +321,41 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
     __syncthreads();                                                         // sync #2
 
     // ---- P2: f layer output, makeError (layer.h:91-95), vectorNorm (Main.cpp:28-34)
-    if (warp == 0) {
-        float d = 0.0f, outv = 0.0f;
+    float dq[PCNN_F];    // TRAIN: d_preact of the f layer, in every thread
+    if (TRAIN) {
+        // Every warp finishes the ten outputs itself (lanes 0..9; 7 + 1 adds, one sigmoid) and broadcasts d_preact by
+        // shuffle: no third block barrier and no shared-memory round trip; warp 0 also keeps the bias / error sums.
+        float d = 0.0f;
         if (lane < PCNN_F) {
             float pre = 0.0f;
 #pragma unroll
             for (int w = 0; w < NWARP; ++w) pre += S.fc_red[w][lane];
             pre += S.params[OFF_FB + lane];                                  // fp_bias_f, layer.h:206-211
-            outv = sigmoid_fast(pre);
-            if (TRAIN) {
-                const int y = S.label[buf];
-                d = (lane == y ? 1.0f : 0.0f) - outv;
-                S.dpre_f[lane] = d;
-                A.gfb += d;
-            } else {
+            const float outv = sigmoid_fast(pre);
+            d = (lane == S.label[buf] ? 1.0f : 0.0f) - outv;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < PCNN_F; ++q) dq[q] = __shfl_sync(0xffffffffu, d, q);
+        if (warp == 0) {
+            A.gfb += d;                                                      // lanes >= 10 add zero
+            float ss = 0.0f;
+#pragma unroll
+            for (int q = 0; q < PCNN_F; ++q) ss = fmaf(dq[q], dq[q], ss);
+            A.err_acc += sqrtf(ss);                                          // every lane holds the same value; lane 0's is used
+        }
+    } else {
+        if (warp == 0) {
+            float outv = 0.0f;
+            if (lane < PCNN_F) {
+                float pre = 0.0f;
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w) pre += S.fc_red[w][lane];
+                pre += S.params[OFF_FB + lane];
+                outv = sigmoid_fast(pre);
                 S.f_out[lane] = outv;
                 if (ev.f_out) ev.f_out[lane] = outv;
             }
-        }
-        if (TRAIN) {
-            __syncwarp();
-            float ss = warp_sum(d * d);
-            if (lane == 0) A.err_acc += sqrtf(ss);
-        } else {
             __syncwarp();
             if (lane == 0) {                                                 // classify(), Main.cpp:193-197
                 int best = 0;
@@ -291,18 +366,16 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
                 if (ev.has_label && best != S.label[buf]) ++A.wrong;
             }
         }
+        return;   // the next image's sync #1 orders the reuse of fc_red / f_out
     }
-    if (!TRAIN) return;   // the next image's sync #1 orders the reuse of fc_red / f_out
-    __syncthreads();                                                         // sync #3
 
     // ---- P3: backward chain (Main.cpp:114-131)
     if (id.worker) {
         float dout_s1 = 0.0f;
 #pragma unroll
         for (int q = 0; q < PCNN_F; ++q) {
-            const float dq = S.dpre_f[q];
-            A.dw_f[q] = fmaf(dq, s1o, A.dw_f[q]);                                          // bp_weight_f, layer.h:214-227
-            dout_s1 = fmaf(S.params[OFF_FW + q * PCNN_S1 + t], dq, dout_s1);                // bp_output_s1, layer.h:237-257
+            A.dw_f[q] = fmaf(dq[q], s1o, A.dw_f[q]);                                       // bp_weight_f, layer.h:214-227
+            dout_s1 = fmaf(fw[q], dq[q], dout_s1);                                          // bp_output_s1, layer.h:237-257
         }
         const float dpre_s1 = dout_s1 * s1o * (1.0f - s1o);                                // bp_preact_s1, layer.h:260-270
         A.bsum_s1 += dpre_s1;                                                               // bp_bias_s1 accumulator, layer.h:303-314
@@ -319,19 +392,16 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
         // bp_weight_c1, layer.h:371-395 (the /576 is applied once in the epilogue)
         const float *ip = S.imgf[buf] + (4 * id.wx) * 28 + 4 * id.wy;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
-            const float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
-            const float x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        for (int i = 0; i < 5; ++i) {
 #pragma unroll
             for (int ox = 0; ox < 4; ++ox) {
-                const int i = r - ox;
-                if (i >= 0 && i < 5) {
+                const float4 lo = *reinterpret_cast<const float4 *>(ip + (ox + i) * 28);
+                const float4 hi = *reinterpret_cast<const float4 *>(ip + (ox + i) * 28 + 4);
+                const float x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-                    for (int j = 0; j < 5; ++j)
+                for (int j = 0; j < 5; ++j)
 #pragma unroll
-                        for (int oy = 0; oy < 4; ++oy) A.dw_c1[i * 5 + j] = fmaf(dpc[ox * 4 + oy], x[oy + j], A.dw_c1[i * 5 + j]);
-                }
+                    for (int oy = 0; oy < 4; ++oy) A.dw_c1[i * 5 + j] = fmaf(dpc[ox * 4 + oy], x[oy + j], A.dw_c1[i * 5 + j]);
             }
         }
     }
@@ -343,6 +413,10 @@ __device__ __forceinline__ void image_pass(FusedSmem<InT> &S, const ThreadId &id
 struct FloatSink {
     float *slot;
     __device__ __forceinline__ void operator()(int p, float v) const { slot[p] = v; }
+};
+struct SmemSink {
+    float *dst;
+    __device__ __forceinline__ void operator()(int p, float v) const { dst[p] = v; }
 };
 struct LLSink {
     llword *slot;

@@ -687,7 +687,7 @@ extern "C" int pcnn_learn_host(pcnn_ctx *ctx, const void *host_images, int pixel
     pcnn_device_guard g(ctx->device);
     if (ctx->step_mode == PCNN_MODE_PERSISTENT)
         PCNN_REQUIRE(use_persistent(ctx), PCNN_ERR_STATE, "persistent mode requested but peers are not attached");
-    if (use_persistent(ctx) && ctx->step_mode != PCNN_MODE_PERSISTENT_BARRIER)
+    if (use_persistent(ctx))
         return learn_host_streamed(ctx, host_images, pixel_type, host_labels, n, B, epochs, mean_err_out);
     return learn_host_chunked(ctx, host_images, pixel_type, host_labels, n, B, epochs, mean_err_out);
 }

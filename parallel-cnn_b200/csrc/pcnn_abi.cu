@@ -73,8 +73,6 @@ extern "C" int pcnn_create(pcnn_ctx **out, int device, void *stream) {
     PCNN_CUDA(cudaMemset(c->d_step_err, 0, STEP_ERR_CAP * sizeof(float)));
     PCNN_CUDA(cudaMalloc(&c->d_step_idx, sizeof(int)));
     PCNN_CUDA(cudaMemset(c->d_step_idx, 0, sizeof(int)));
-    PCNN_CUDA(cudaMalloc(&c->d_bar, sizeof(unsigned)));
-    PCNN_CUDA(cudaMemset(c->d_bar, 0, sizeof(unsigned)));
     PCNN_CUDA(cudaMalloc(&c->d_abort, sizeof(int)));
     PCNN_CUDA(cudaMemset(c->d_abort, 0, sizeof(int)));
     PCNN_CUDA(cudaMemset(c->d_params, 0, NPACK * sizeof(float)));
@@ -117,7 +115,6 @@ extern "C" int pcnn_destroy(pcnn_ctx *ctx) {
     if (ctx->h_hs_tag) cudaFreeHost(ctx->h_hs_tag);
     if (ctx->d_slots_ll) cudaFree(ctx->d_slots_ll);
     if (ctx->d_params_ll) cudaFree(ctx->d_params_ll);
-    if (ctx->d_bar) cudaFree(ctx->d_bar);
     if (ctx->d_abort) cudaFree(ctx->d_abort);
     for (auto &kv : ctx->graphs) cudaGraphExecDestroy(kv.second);
     ctx->graphs.clear();

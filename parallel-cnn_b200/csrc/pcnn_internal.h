@@ -11,7 +11,6 @@
 #include "../../include/pcnn.h"
 
 #define PCNN_VERSION_NUMBER 200   /* 0.2.0 */
-#define PCNN_MODE_PERSISTENT_BARRIER 3   /* internal A/B switch: the round-1 grid-barrier kernel */
 
 // Packed vectors on the device carry one extra float: the batch sum of per-sample error norms.
 constexpr int NPARAM = PCNN_NPARAM;
@@ -110,7 +109,10 @@ struct pcnn_ctx {
     int step_mode = PCNN_MODE_AUTO;
     int persist_cap = 0;                    // co-resident CTAs of k_train_persist on this device
     bool persist_used = false;
-    unsigned *d_bar = nullptr;              // grid barrier counter
+    int persist_cluster_cap = 0;            // co-resident CTAs when launched as clusters of 8
+    bool persist_no_coop = false;           // the driver refused cooperative + cluster launches
+    int persist_force_cluster = 0;          // > 0: cap the cluster size (A/B measurements through pcnn_persist_tune)
+    int persist_last_cluster = 0, persist_last_grid = 0;
     int *d_abort = nullptr;                 // set by a spin loop that ran out of budget
     long long *d_trace = nullptr;           // optional phase timestamps of the persistent kernel (pcnn_persist_trace)
     unsigned p2p_step_id = 0;               // distributed steps issued since pcnn_p2p_attach (tags of the peer exchange)

@@ -1,27 +1,13 @@
-// parallel-cnn_b200/csrc/persist_kernels.cu -- the whole training loop as ONE persistent cooperative kernel.
-//
-// k_train_persist runs `nsteps` consecutive mini-batch steps without returning to the host.  Per step every CTA
-//   1. runs forward + backward for its images of the batch (fused_body.cuh, parameters in shared memory),
-//   2. publishes its packed partial gradient (slot), grid barrier,
-//   3. reduces ITS chunk of the packed vector over all slots in a fixed order (deterministic, no atomics),
-//      [N > 1: pushes the chunk into every peer GPU's inbox over NVLink (plain stores to IPC-mapped peer memory +
-//       a release flag), waits for the same chunk from every rank and adds them in rank order -- a fused
-//       reduce-scatter/all-gather with 2,344 floats per GPU per step and no second kernel],
-//      applies the SGD update to its chunk of the global parameters, grid barrier,
-//   4. reloads the 9.4 KB parameter block with a TMA bulk copy (overlapped with the next image's conversion).
-// The next step's first image is prefetched before the barriers, the sample cursor lives in registers, and launch
-// overhead, cursor kernels and per-step parameter prologues of the graph path disappear.  Cooperative launch
-// guarantees co-residency of the grid (2 CTAs/SM); every spin loop has a cycle budget and raises an abort flag
-// instead of hanging the GPU.
-//
-// Determinism: slot order, chunk order and rank order are fixed, so replicas stay bit-identical and reruns reproduce.
+// parallel-cnn_b200/csrc/persist_kernels.cu -- the whole training loop as ONE persistent kernel (k_train_persist below):
+// `nsteps` consecutive mini-batch steps without returning to the host, the gradient reduction, the SGD update, the
+// multi-GPU exchange and the parameter broadcast all inside the kernel.  Round 1 synchronised the steps with two fenced
+// grid barriers; this version is a dataflow over thread-block clusters, asynchronous distributed-shared-memory stores and
+// tagged words in L2 (A/B numbers of both: profiles/r02_persist_phase_trace_ab.jsonl).
 #include "fused_body.cuh"
 
 using namespace pcnn_fused;
 
 namespace {
-
-constexpr long long SPIN_BUDGET = 6000000000LL;   // ~3 s at 2 GHz
 
 struct PersistArgs {
     const void *images;
@@ -29,8 +15,6 @@ struct PersistArgs {
     long long n_total;
     float *params;            // global packed parameters, updated in place every step
     float *grads;             // packed gradient (+ error sum) of the most recent step
-    float *slots;             // [grid][NPACK]
-    unsigned *bar;            // grid barrier counter, zeroed by the host before the launch
     long long *cursor;        // in/out: global sample position
     double *err_total;
     float *step_err;          // ring [STEP_ERR_CAP]
@@ -61,26 +45,7 @@ __device__ __forceinline__ long long globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
     return v;
 }
-// phase boundaries of one step as seen by CTA 0: 0 step start, 1 images done, 2 slot published, 3 barrier 1 passed,
-// 4 chunk reduced/exchanged/updated, 5 barrier 2 passed
-#define PCNN_TRACE(k)                                                                              \
-    do {                                                                                           \
-        if (a.trace && c == 0 && t == 0 && s < PCNN_TRACE_STEPS) a.trace[s * 6 + (k)] = globaltimer_ns(); \
-    } while (0)
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // {value, step id} words of the peer exchange: one 8-byte volatile access each way (bypasses L1, single-copy atomic)
 __device__ __forceinline__ void st_ll(uint2 *p, float value, unsigned id) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(value)), "r"(id) : "memory");
@@ -90,303 +55,129 @@ __device__ __forceinline__ uint2 ld_ll(const uint2 *p) {
     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void red_release_gpu_add(unsigned *p, unsigned v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// all CTAs of the (co-resident) grid; `target` = arrivals expected so far
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned target, int *abort_flag) {
-    __syncthreads();
-    if (gridDim.x == 1) return;        // a single CTA: the block barrier is the grid barrier
-    if (threadIdx.x == 0) {
-        // release-add: cumulative over the CTA's writes ordered before it by the block barrier above
-        red_release_gpu_add(bar, 1u);
-        const long long t0 = clock64();
-        while (ld_acquire_gpu(bar) < target) {
-            if (*(volatile int *)abort_flag) break;
-            if (clock64() - t0 > SPIN_BUDGET) { *(volatile int *)abort_flag = 1; break; }
-        }
-    }
-    __syncwarp();      // lane 0 rejoins its warp before the block barrier
-    __syncthreads();
-}
-
-template <typename InT>
-__global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist_bar(const PersistArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    FusedSmem<InT> &S = *reinterpret_cast<FusedSmem<InT> *>(smem_raw);
-    const ThreadId id;
-    const int t = id.t;
-    const int G = gridDim.x, c = blockIdx.x;
-    const InT *images = reinterpret_cast<const InT *>(a.images);
-
-    // reduce-phase geometry: this CTA owns packed entries [e0, e0 + cnt)
-    const int chunk = (NPACK + G - 1) / G;
-    const int e0 = c * chunk;
-    const int cnt = e0 >= NPACK ? 0 : (e0 + chunk > NPACK ? NPACK - e0 : chunk);
-    const int PH = chunk >= NT ? 1 : NT / chunk;         // slot phases when the chunk is narrower than the CTA
-
-    long long cursor = *a.cursor;
-    const int step_idx0 = *a.step_idx;
-    const long long stride = a.rank_local ? (long long)a.B : (long long)a.B * a.world;
-    auto shard = [&](long long cur, long long &base, int &nb) {
-        base = cur + (a.rank_local ? 0 : (long long)a.rank * a.B);
-        const long long avail = a.n_total - base;
-        nb = avail <= 0 ? 0 : (avail < a.B ? (int)avail : a.B);
-    };
-    long long base;
-    int nb;
-    shard(cursor, base, nb);
-
-    init_barriers(S);
-    int li = 0;                 // CTA-local running image counter (staging buffer + mbarrier phase)
-    unsigned pphase = 0;        // uses of the parameter barrier
-    unsigned nbar = 0;          // grid barriers passed
-    if (t == 0) {
-        issue_params(S, a.params);
-        if (c < nb) issue_image(S, 0, images + (base + c) * PCNN_IMG);
-    }
-    __syncwarp();   // lane 0 rejoins its warp (see image_pass)
-
-    for (int s = 0; s < a.nsteps; ++s) {
-        // ---- 1. forward + backward over this CTA's images
-        PCNN_TRACE(0);
-        Acc A;
-        A.zero();
-        const InT *img_base = images + base * PCNN_IMG;
-        const uint8_t *lab_base = a.labels + base;
-        bool first = true;
-        const EvalOut ev = {nullptr, nullptr, true};
-        for (int b = c; b < nb; b += G, ++li) {
-            const int bn = b + G;
-            image_pass<InT, true>(S, id, li, lab_base + b, bn < nb ? img_base + (long long)bn * PCNN_IMG : nullptr,
-                                  first ? (int)(pphase & 1) : -1, A, ev);
-            first = false;
-        }
-        if (first) mbar_wait(&S.mbar[2], pphase & 1);   // image-less CTAs still consume this parameter phase
-        ++pphase;
-        PCNN_TRACE(1);
-        cta_epilogue(S, id, A, FloatSink{a.slots + (long long)c * NPACK});
-        PCNN_TRACE(2);
-
-        // position of the next step; its first image is prefetched across the barriers
-        long long ncur = cursor + stride;
-        if (ncur >= a.n_total) ncur = 0;
-        long long nbase;
-        int nnb;
-        shard(ncur, nbase, nnb);
-        const bool more = s + 1 < a.nsteps;
-        if (t == 0 && more && c < nnb) issue_image(S, li & 1, images + (nbase + c) * PCNN_IMG);
-        __syncwarp();
-
-        nbar += 1;
-        grid_barrier(a.bar, nbar * (unsigned)G, a.abort_flag);                 // all slots published
-        PCNN_TRACE(3);
-
-        // ---- 2. fixed-order reduction of my chunk over all slots (entry e of the chunk is owned by thread e % NT)
-        float *part = S.red;                                                   // [PH][chunk] when chunk < NT
-        const float step = a.dt / (float)effective_global_batch(cursor, true, a.n_total, a.B, a.world, a.rank_local);
-        const unsigned stepid = a.step_base + (unsigned)s + 1u;
-        const int par = (int)(stepid & 1u);
-        auto finalize = [&](int p, float g, float w_old) {
-            a.grads[p] = g;
-            if (p < NPARAM) {
-                a.params[p] = updated_entry(w_old, p, g, step);
-            } else {
-                *a.err_total += (double)g;
-                a.step_err[(step_idx0 + s) & (STEP_ERR_CAP - 1)] = g;
-            }
-        };
-        // Peer exchange, "low-latency" style: every 8-byte inbox word carries {value, step id}.  An 8-byte store is
-        // single-copy atomic, so the receiver needs no flag round trip and the sender no system-scope fence: it polls
-        // the word until the step id matches.  One NVLink one-way latency per step.
-        auto publish = [&](int p, float g, float w_old) {                      // local result of one owned entry
-            if (a.world > 1) {
-                for (int q = 0; q < a.world; ++q)
-                    st_ll(a.peer_inbox[q] + ((long long)par * a.world + a.rank) * NPACK + p, g, stepid);
-            } else {
-                finalize(p, g, w_old);
-            }
-        };
-        constexpr int MAXE = (NPACK + NT - 1) / NT;                            // entries a thread can own (G == 1)
-        float w_mine[MAXE];                                                    // old parameter values, requested early
-        if (chunk < NT) {
-            const int e = t % chunk, ph = t / chunk;
-            w_mine[0] = (t < cnt && e0 + t < NPARAM) ? __ldcg(a.params + e0 + t) : 0.0f;
-            float sum = 0.0f;
-            if (e < cnt && ph < PH) {
-                const float *sp = a.slots + e0 + e;
-                for (int k0 = ph; k0 < G; k0 += 8 * PH) {                      // 8 loads in flight, added in slot order
-                    float v[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int k = k0 + u * PH;
-                        v[u] = k < G ? __ldcg(sp + (long long)k * NPACK) : 0.0f;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) sum += v[u];
-                }
-            }
-            if (ph < PH) part[ph * chunk + e] = sum;
-            __syncthreads();
-            if (t < cnt) {
-                float g = part[t];
-                for (int q = 1; q < PH; ++q) g += part[q * chunk + t];
-                publish(e0 + t, g, w_mine[0]);
-            }
-        } else {                                                               // G <= 10: a thread owns up to MAXE entries
-            float gs[MAXE];
-#pragma unroll
-            for (int i = 0; i < MAXE; ++i) {
-                const int e = t + i * NT;
-                gs[i] = 0.0f;
-                w_mine[i] = 0.0f;
-                if (e < cnt) {
-                    const int p = e0 + e;
-                    if (p < NPARAM) w_mine[i] = __ldcg(a.params + p);
-                    float acc = 0.0f;
-                    for (int k = 0; k < G; ++k) acc += __ldcg(a.slots + (long long)k * NPACK + p);
-                    gs[i] = acc;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < MAXE; ++i)
-                if (t + i * NT < cnt) publish(e0 + t + i * NT, gs[i], w_mine[i]);
-        }
-        if (a.world > 1 && cnt > 0) {
-            // ---- 2b. collect every rank's value of my entries (they arrive over NVLink) and add them in rank order
-#pragma unroll
-            for (int i = 0; i < MAXE; ++i) {
-                const int e = t + i * NT;
-                if (e >= cnt) break;
-                // Every polling round requests the words of ALL ranks still missing at once (independent loads, one L2 round
-                // trip per round) instead of waiting for rank 0, then rank 1, ...: the values of the ranks arrive within a
-                // fraction of a microsecond of each other, so after the first one is in, one more round collects the rest
-                // (measured at 4 GPUs in one session: 13.10 vs 13.29 us per step).
-                const uint2 *w0 = a.inbox + (long long)par * a.world * NPACK + e0 + e;
-                uint2 v[PCNN_MAX_PEERS];
-                unsigned pending = (1u << a.world) - 1u;
-                const long long t0 = clock64();
-                while (pending) {
-#pragma unroll
-                    for (int q = 0; q < PCNN_MAX_PEERS; ++q)
-                        if ((pending >> q) & 1u) v[q] = ld_ll(w0 + (long long)q * NPACK);
-#pragma unroll
-                    for (int q = 0; q < PCNN_MAX_PEERS; ++q)
-                        if (((pending >> q) & 1u) && v[q].y == stepid) pending &= ~(1u << q);
-                    if (pending) {
-                        if (*(volatile int *)a.abort_flag) break;
-                        if (clock64() - t0 > 4 * SPIN_BUDGET) { *(volatile int *)a.abort_flag = 2; break; }
-                    }
-                }
-                float g = 0.0f;
-#pragma unroll
-                for (int q = 0; q < PCNN_MAX_PEERS; ++q)                       // rank order: identical on all GPUs
-                    if (q < a.world) g += __uint_as_float(v[q].x);
-                finalize(e0 + e, g, w_mine[i]);
-            }
-            __syncwarp();
-        }
-        asm volatile("fence.proxy.async.global;" ::: "memory");               // parameter stores -> later bulk-copy reads
-        PCNN_TRACE(4);
-
-        nbar += 1;
-        grid_barrier(a.bar, nbar * (unsigned)G, a.abort_flag);                 // parameters updated everywhere
-        PCNN_TRACE(5);
-        if (t == 0 && more) {
-            asm volatile("fence.proxy.async.global;" ::: "memory");
-            issue_params(S, a.params);
-        }
-        __syncwarp();
-        cursor = ncur;
-        base = nbase;
-        nb = nnb;
-    }
-    if (c == 0 && t == 0) {
-        *a.cursor = cursor;
-        *a.step_idx = step_idx0 + a.nsteps;
-    }
-}
-
 
 // =====================================================================================================================
-// k_train_persist -- the dataflow version: no grid barrier, no fence on the critical path.
+// k_train_persist -- the dataflow version: thread-block clusters, asynchronous distributed-shared-memory stores and
+// tagged words through L2; no grid barrier, no cluster barrier and no fence inside the step loop.
 //
-// Every buffer that crosses CTAs holds tagged 64-bit words {fp32 value, step id} (fused_body.cuh: ll_store / ll_load);
-// a consumer polls the words it needs until they carry the id it expects.  Per step X every CTA
-//   1. copies the tagged parameters (tag X) from L2 into shared memory,
+// Inside a cluster (CS = 8 CTAs) data is PUSHED into the consumer's shared memory with st.async, which signals the
+// consumer's mbarrier with the byte count (the mechanism of a bulk copy): the consumer just waits on its own mbarrier.
+// Between clusters data moves through L2 as tagged 64-bit words {fp32 value, step id} (fused_body.cuh: ll_store /
+// ll_load) that the consumer polls until they carry the id it expects.  Per step X every CTA (cluster rank r)
+//   1. polls share r (1/CS) of the tagged parameters (tag X) and pushes it into S.params of all CS CTAs; waits until its
+//      own S.params is complete (mbarrier, 9,376 bytes),
 //   2. runs forward + backward over its images,
-//   3. reduces its register accumulators and writes its tagged partial gradient (slot, tag X),
-//   4. as OWNER of a chunk of the packed vector: gathers that chunk from all slots (tag X), adds them in slot order,
-//      [N > 1: exchanges the chunk with the peer GPUs, rank order], updates its parameters -- which it keeps in
+//   3. reduces its register accumulators and pushes piece q of the packed gradient to cluster rank q (S.recv[r]),
+//   4. waits for the CS pieces of ITS share (mbarrier), adds them in rank order and writes them, tagged X, to the
+//      cluster's slot in L2,
+//   5. as OWNER of a chunk of the packed vector: gathers that chunk from all cluster slots (tag X), adds them in slot
+//      order, [N > 1: exchanges the chunk with the peer GPUs, rank order], updates its parameters -- which it keeps in
 //      registers for the whole launch -- and publishes them with tag X + 1.
-// Two L2 round trips per step instead of two fenced grid barriers.  Buffer reuse needs no extra synchronisation: a CTA
-// can only overwrite its slot (step X + 1) after it has fetched ALL parameters tagged X + 1, i.e. after every owner has
-// finished reading the slots of step X; an owner can only overwrite its parameters (tag X + 2) after it has read all
-// slots of step X + 1, i.e. after every CTA has fetched the parameters tagged X + 1.
-// Determinism: slot order, phase order and rank order are fixed -> bit-identical reruns and replicas.
+// Buffer reuse needs no extra synchronisation: a CTA can only reach the next use of a buffer after it has received the
+// parameters tagged X + 1, i.e. after every owner has read all cluster slots of step X, i.e. after every CTA of every
+// cluster has consumed what was pushed to it in step X.
+// Determinism: rank order, slot order and phase order are fixed -> bit-identical reruns and replicas.
 // =====================================================================================================================
-// phase boundaries of one step as seen by CTA 0: 0 step start, 1 parameters resident, 2 images done, 3 slot published,
-// 4 owned chunk reduced (and exchanged), 5 parameters published
+// phase boundaries of one step as seen by CTA 0: 0 step start, 1 parameters resident, 2 images done, 3 cluster slot
+// written, 4 owned chunk gathered, 5 parameters published
+// dataflow kernel: CTA 0 stamps every step (row s of the trace), and at step PCNN_TRACE_STEPS / 2 EVERY CTA stamps its own
+// row (8 values: the 6 phase stamps, its SM id, spare) behind them -- the spread over CTAs is the skew the owners wait for
+#define PCNN_TRACE2(k)                                                  \
+    do {                                                                \
+        if (t == 0) {                                                   \
+            const long long now__ = globaltimer_ns();                   \
+            if (tr0) tr0[(k)] = now__;                                  \
+            if (tr1) tr1[(k)] = now__;                                  \
+        }                                                               \
+    } while (0)
+
 constexpr long long POLL_BUDGET = 4000000000LL;   // cycles a single wait may take before the launch is aborted
 
+// Budget of one wait.  Once any wait has given up (here or in another CTA: global abort flag) every later wait of this CTA
+// returns at once (shared-memory flag), so an aborted launch drains in milliseconds instead of hanging the GPU.  No CTA
+// ever leaves the step loop early: the hardware cluster barriers need all of them.
 struct PollGuard {
     long long t0;
     unsigned n;
     int *abort_flag;
-    __device__ __forceinline__ explicit PollGuard(int *f) {
+    volatile int *local;
+    __device__ __forceinline__ PollGuard(int *f, int *cta_flag) {
         t0 = clock64();
         n = 0;
         abort_flag = f;
+        local = cta_flag;
     }
-    // true: give up (somebody aborted or this wait ran out of budget)
+    // true: give up
     __device__ __forceinline__ bool expired(int code) {
-        if ((++n & 1023u) != 0) return false;
-        if (*(volatile int *)abort_flag) return true;
-        if (clock64() - t0 > POLL_BUDGET) { *(volatile int *)abort_flag = code; return true; }
+        if ((++n & 255u) != 0) return false;
+        if (*local) return true;
+        if (*(volatile int *)abort_flag) { *local = 1; return true; }
+        if (clock64() - t0 > POLL_BUDGET) { *(volatile int *)abort_flag = code; *local = 1; return true; }
         return false;
     }
 };
 
-// all threads: tagged parameters -> S.params (ordered before the readers by the next block barrier)
-template <typename InT>
-__device__ __forceinline__ void fetch_params_ll(FusedSmem<InT> &S, const llword *pll, unsigned tag, int *abort_flag) {
-    constexpr int NPAIR = NPACK / 2;                          // 1172 16-byte pairs
-    constexpr int ROUNDS = (NPAIR + NT - 1) / NT;             // 6
+// mbarrier wait that gives up with the launch (same budget as the polling loops)
+__device__ __forceinline__ void mbar_wait_guarded(unsigned long long *bar, unsigned parity, PollGuard &guard) {
+    for (;;) {
+        unsigned done;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (done || guard.expired(1)) return;
+    }
+}
+
+// share `rank` of the packed vector among CS cluster ranks: [rank * SH, rank * SH + len), SH even (moved in pairs)
+template <int CS> struct Share {
+    static constexpr int SH = ((NPACK + CS - 1) / CS + 1) & ~1;
+    __device__ __forceinline__ static int len(unsigned rank) {
+        const int b = (int)rank * SH;
+        return b >= NPACK ? 0 : (b + SH > NPACK ? NPACK - b : SH);
+    }
+};
+
+// Step 1: poll this rank's share of the tagged parameters and push every pair into S.params of ALL CTAs of the cluster;
+// then wait until this CTA's own S.params has received all NPACK floats (thread 0 armed the mbarrier for them).
+template <typename InT, int CS>
+__device__ __forceinline__ void fetch_params_cluster(FusedSmem<InT> &S, const llword *pll, unsigned tag, unsigned crank, unsigned parity,
+                                                     int *abort_flag) {
     static_assert(NPACK % 2 == 0, "pairs");
-    const int t = threadIdx.x;
-    float2 *dst = reinterpret_cast<float2 *>(S.params);
-    PollGuard guard(abort_flag);
-    {   // stage 1: poll ONE pair per thread until the owners have published (keeps the idle polling traffic at 1/6)
+    const int sb = (int)crank * Share<CS>::SH, sl = Share<CS>::len(crank);
+    PollGuard guard(abort_flag, &S.aborted);
+    for (int i = threadIdx.x; i < sl / 2; i += NT) {
         float v0, v1;
         unsigned g0, g1;
         for (;;) {
-            ll_load2(pll + 2 * t, v0, g0, v1, g1);
-            if (g0 == tag && g1 == tag) break;
-            if (guard.expired(1)) break;
+            ll_load2(pll + sb + 2 * i, v0, g0, v1, g1);
+            if ((g0 == tag && g1 == tag) || guard.expired(1)) break;
         }
-        dst[t] = make_float2(v0, v1);
+        float *dst = S.params + sb + 2 * i;
+        if (CS == 1) {
+            *reinterpret_cast<float2 *>(dst) = make_float2(v0, v1);       // published by the image pass's first block barrier
+        } else {
+#pragma unroll
+            for (unsigned q = 0; q < (unsigned)CS; ++q) dsmem_st_async_f2(dsmem_addr(dst, q), v0, v1, dsmem_addr(&S.mbar[2], q));
+        }
     }
-    // stage 2: the remaining pairs, all loads in flight at once; stragglers are re-polled
-    float v0[ROUNDS - 1], v1[ROUNDS - 1];
-    unsigned pend = 0;
-#pragma unroll
-    for (int j = 1; j < ROUNDS; ++j)
-        if (t + j * NT < NPAIR) pend |= 1u << j;
-    while (pend) {
-        unsigned g0[ROUNDS - 1], g1[ROUNDS - 1];
-#pragma unroll
-        for (int j = 1; j < ROUNDS; ++j)
-            if ((pend >> j) & 1u) ll_load2(pll + 2 * (t + j * NT), v0[j - 1], g0[j - 1], v1[j - 1], g1[j - 1]);
-#pragma unroll
-        for (int j = 1; j < ROUNDS; ++j)
-            if (((pend >> j) & 1u) && g0[j - 1] == tag && g1[j - 1] == tag) {
-                dst[t + j * NT] = make_float2(v0[j - 1], v1[j - 1]);
-                pend &= ~(1u << j);
-            }
-        if (pend && guard.expired(1)) break;
-    }
+    if (CS > 1) mbar_wait_guarded(&S.mbar[2], parity, guard);
 }
+
+// gradient piece sink of the CTA epilogue: entry p goes to the cluster rank that owns its share
+template <typename InT, int CS> struct PushSink {
+    FusedSmem<InT> *S;
+    unsigned crank;
+    __device__ __forceinline__ void operator()(int p, float v) const {
+        if (CS == 1) {
+            S->recv[p] = v;
+            return;
+        }
+        const unsigned q = (unsigned)p / (unsigned)Share<CS>::SH;
+        const int i = p - (int)q * Share<CS>::SH;
+        dsmem_st_async_f32(dsmem_addr(S->recv + (int)crank * Share<CS>::SH + i, q), v, dsmem_addr(&S->mbar[3], q));
+    }
+};
 
 // thread 0: wait until the host-streamed chunk holding `src` has landed (pcnn_learn_host), then make the DMA-written
 // bytes visible to the async proxy that the bulk copy reads through.  The gate's constants live in shared memory.
@@ -399,36 +190,37 @@ template <typename InT> struct ChunkGate {
         const long long first = S->gate_first;
         const unsigned *f = ready + (sample < first ? 0 : 1 + (sample - first) / S->gate_chunk);
         const unsigned want = S->gate_tag;
-        PollGuard guard(S->gate_abort);
+        PollGuard guard(S->gate_abort, &S->aborted);
         while (*(const volatile unsigned *)f != want)
             if (guard.expired(3)) break;
         asm volatile("fence.proxy.async.global;" ::: "memory");
     }
 };
 
-// Steps 2 and 3 of a step: forward + backward over this CTA's images b = c, c + G, ... < nb, then the CTA reduction into
-// the tagged slot.  Deliberately NOT inlined: the register allocation of the image pass (accumulators + patch rows, right
-// at the 128-register budget of 2 CTAs/SM) then does not compete with the persistent loop's own state.  Returns the
-// advanced CTA-local image counter.
-template <typename InT>
-__device__ __noinline__ int step_images(FusedSmem<InT> *Sp, const InT *img_base, const uint8_t *lab_base, int c, int G, int nb,
-                                        int li, llword *slot, unsigned tag, long long *trace_row) {
-    FusedSmem<InT> &S = *Sp;
-    const ThreadId id;
-    const ChunkGate<InT> gate{Sp};
+// Steps 2 and 3 of a step: forward + backward over this CTA's images b = c, c + G, ... < nb, then the CTA reduction whose
+// results are pushed piece-wise to the cluster ranks.  Returns the advanced CTA-local image counter.
+template <typename InT, int CS>
+__device__ __forceinline__ int step_images(FusedSmem<InT> &S, const ThreadId &id, const InT *img_base, const uint8_t *lab_base, int c, int G,
+                                           int nb, int li, unsigned crank, long long *trace_row, long long *trace_row2) {
+    const ChunkGate<InT> gate{&S};
     Acc A;
     A.zero();
     const EvalOut ev = {nullptr, nullptr, true};
     for (int b = c; b < nb; b += G, ++li) {
         const int bn = b + G;
-        image_pass<InT, true>(S, id, li, lab_base + b, bn < nb ? img_base + (long long)bn * PCNN_IMG : nullptr, -1, A, ev, gate);
+        // the step's first image was prepared (landed + converted) while the CTA was waiting for the parameters
+        image_pass<InT, true>(S, id, li, lab_base + b, bn < nb ? img_base + (long long)bn * PCNN_IMG : nullptr, -1, A, ev, gate, b == c);
     }
-    if (trace_row && id.t == 0) trace_row[2] = globaltimer_ns();
-    cta_epilogue(S, id, A, LLSink{slot, tag});
+    if (id.t == 0 && (trace_row || trace_row2)) {
+        const long long now = globaltimer_ns();
+        if (trace_row) trace_row[2] = now;
+        if (trace_row2) trace_row2[2] = now;
+    }
+    cta_epilogue(S, id, A, PushSink<InT, CS>{&S, crank});
     return li;
 }
 
-template <typename InT>
+template <typename InT, int CS>
 __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const PersistArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem<InT> &S = *reinterpret_cast<FusedSmem<InT> *>(smem_raw);
@@ -444,15 +236,21 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         S.gate_first = a.ready_first;
         S.gate_abort = a.abort_flag;
         S.gate_tag = a.ready_tag;
+        S.aborted = 0;
     }
 
-    // owner geometry: this CTA owns packed entries [e0, e0 + cnt); thread t owns entries e0 + t + i * NT
+    // cluster geometry (CS = 1: launched without a cluster dimension, every CTA is its own cluster)
+    const unsigned crank = CS == 1 ? 0u : cluster_ctarank();
+    const int NC = G / CS;                                // clusters = slots
+    const int my_sb = (int)crank * Share<CS>::SH, my_sl = Share<CS>::len(crank);
+    llword *cslot = a.slots_ll + (long long)(CS == 1 ? (unsigned)c : cluster_idx()) * NPACK;
+    // owner geometry: this CTA owns packed entries [e0, e0 + cnt); thread t owns entry e0 + t (wide chunks: + i * NT)
     const int chunk = (NPACK + G - 1) / G;
     const int e0 = c * chunk;
     const int cnt = e0 >= NPACK ? 0 : (e0 + chunk > NPACK ? NPACK - e0 : chunk);
     const int PH = chunk >= NT ? 1 : NT / chunk;         // slot phases when the chunk is narrower than the CTA
-    constexpr int MAXE = (NPACK + NT - 1) / NT;          // entries a thread can own (G == 1)
-    constexpr int KB = 12;                               // slot words one thread keeps in flight
+    constexpr int KB = 8;                                // slot words one thread keeps in flight
+    const int PHG = PH < (NC + KB - 1) / KB ? PH : (NC + KB - 1) / KB;   // phases in use: thread (e, ph) adds slots ph, ph + PHG, ...
 
     long long cursor = (a.fresh & 1) ? 0 : *a.cursor;
     const int step_idx0 = (a.fresh & 1) ? 0 : *a.step_idx;
@@ -466,7 +264,14 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
     int nb;
     shard(cursor, base, nb);
 
+    if (CS > 1 && cluster_nctarank() != (unsigned)CS) {
+        // launched without the cluster dimension this instantiation is built for (seen under profilers that re-issue the
+        // launch): every CTA takes this exit, nothing has been signalled yet
+        if (t == 0) *(volatile int *)a.abort_flag = 4;
+        return;
+    }
     init_barriers(S);
+    if (CS > 1) cluster_sync_all();   // every CTA's mbarriers are initialised before a peer may signal them
     int li = 0;                 // CTA-local running image counter (staging buffer + mbarrier phase)
     if (t == 0 && c < nb) {
         const InT *src = images + (base + c) * PCNN_IMG;
@@ -488,16 +293,43 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
 
     for (int s = 0; s < a.nsteps; ++s) {
         const unsigned tag = a.step_base + (unsigned)s + 1u;
-        if ((s & 63) == 63 && *(volatile int *)a.abort_flag) break;            // somebody gave up: leave quickly
-        PCNN_TRACE(0);
-        // ---- 1. this step's parameters: L2 -> shared memory (the first block barrier of the image pass orders them)
-        fetch_params_ll(S, a.params_ll, tag, a.abort_flag);
-        PCNN_TRACE(1);
+        long long *tr0 = (a.trace && c == 0 && s < PCNN_TRACE_STEPS) ? a.trace + s * 6 : nullptr;
+        long long *tr1 = (a.trace && s == PCNN_TRACE_STEPS / 2) ? a.trace + PCNN_TRACE_STEPS * 6 + c * 8 : nullptr;
+        if (tr1 && t == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            tr1[6] = (long long)smid;
+        }
+        PCNN_TRACE2(0);
+        // ---- 1. this step's parameters: my share L2 -> shared memory of the whole cluster.  Thread 0 arms both
+        //         mbarriers of the step: all NPACK parameters, and CS pieces of my gradient share
+        if (CS > 1 && t == 0) {
+            mbar_expect_tx(&S.mbar[2], NPACK * 4);
+            mbar_expect_tx(&S.mbar[3], (unsigned)(CS * my_sl * 4));
+        }
+        __syncwarp();
+        // the step's first image has been in flight since the previous step: land + convert it while the owners publish
+        if (c < nb) image_prepare(S, id, li, a.labels + base + c);
+        fetch_params_cluster<InT, CS>(S, a.params_ll, tag, crank, (unsigned)s & 1u, a.abort_flag);
+        PCNN_TRACE2(1);
 
-        // ---- 2. forward + backward over this CTA's images, 3. CTA reduction -> tagged slot
-        li = step_images<InT>(&S, images + base * PCNN_IMG, a.labels + base, c, G, nb, li, a.slots_ll + (long long)c * NPACK, tag,
-                              (a.trace && c == 0 && s < PCNN_TRACE_STEPS) ? a.trace + s * 6 : nullptr);
-        PCNN_TRACE(3);
+        // ---- 2. forward + backward over this CTA's images, 3. CTA reduction, pieces pushed to the cluster ranks
+        li = step_images<InT, CS>(S, id, images + base * PCNN_IMG, a.labels + base, c, G, nb, li, crank,
+                                  tr0, tr1);
+
+        // ---- 4. my share: the CS pieces (rank order) -> tagged cluster slot
+        {
+            PollGuard guard(a.abort_flag, &S.aborted);
+            if (CS > 1) mbar_wait_guarded(&S.mbar[3], (unsigned)s & 1u, guard);
+            else __syncthreads();
+            for (int i = t; i < my_sl; i += NT) {
+                float g = 0.0f;
+#pragma unroll
+                for (int q = 0; q < CS; ++q) g += S.recv[q * Share<CS>::SH + i];
+                ll_store(cslot + my_sb + i, g, tag);
+            }
+        }
+        PCNN_TRACE2(3);
 
         // position of the next step; its first image is prefetched while the gradient is being reduced
         long long ncur = cursor + stride;
@@ -529,7 +361,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
                 const uint2 *w0p = a.inbox + (long long)par * a.world * NPACK + p;
                 uint2 v[PCNN_MAX_PEERS];
                 unsigned pending = (1u << a.world) - 1u;
-                PollGuard guard(a.abort_flag);
+                PollGuard guard(a.abort_flag, &S.aborted);
                 while (pending) {
 #pragma unroll
                     for (int q = 0; q < PCNN_MAX_PEERS; ++q)
@@ -560,30 +392,22 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         if (chunk < NT) {
             const int e = t % chunk, ph = t / chunk;
             float sum = 0.0f;
-            if (e < cnt && ph < PH) {
+            if (e < cnt && ph < PHG) {
                 const llword *sp = a.slots_ll + e0 + e;
-                PollGuard guard(a.abort_flag);
-                {   // wait for my first word before requesting the rest (bounds the idle polling traffic)
-                    float v;
-                    unsigned g;
-                    for (;;) {
-                        ll_load(sp + (long long)ph * NPACK, v, g);
-                        if (g == tag || guard.expired(1)) break;
-                    }
-                }
-                for (int k0 = ph; k0 < G; k0 += KB * PH) {
+                PollGuard guard(a.abort_flag, &S.aborted);
+                for (int k0 = ph; k0 < NC; k0 += KB * PHG) {
                     float v[KB];
                     unsigned pend = 0;
 #pragma unroll
                     for (int u = 0; u < KB; ++u) {
                         v[u] = 0.0f;
-                        if (k0 + u * PH < G) pend |= 1u << u;
+                        if (k0 + u * PHG < NC) pend |= 1u << u;
                     }
                     while (pend) {
                         unsigned g[KB];
 #pragma unroll
                         for (int u = 0; u < KB; ++u)
-                            if ((pend >> u) & 1u) ll_load(sp + (long long)(k0 + u * PH) * NPACK, v[u], g[u]);
+                            if ((pend >> u) & 1u) ll_load(sp + (long long)(k0 + u * PHG) * NPACK, v[u], g[u]);
 #pragma unroll
                         for (int u = 0; u < KB; ++u)
                             if (((pend >> u) & 1u) && g[u] == tag) pend &= ~(1u << u);
@@ -593,23 +417,23 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
                     for (int u = 0; u < KB; ++u) sum += v[u];                  // slot order within the phase
                 }
             }
-            if (ph < PH) S.part[ph * chunk + e] = sum;
+            if (ph < PHG) S.part[ph * chunk + e] = sum;
             __syncthreads();
-            PCNN_TRACE(4);
+            PCNN_TRACE2(4);
             if (t < cnt) {
                 float g = S.part[t];
-                for (int q = 1; q < PH; ++q) g += S.part[q * chunk + t];       // phase order
+                for (int q = 1; q < PHG; ++q) g += S.part[q * chunk + t];      // phase order
                 w0 = finalize(e0 + t, g, w0);
             }
         } else {                                                               // G <= 10: a thread owns several entries
-            PCNN_TRACE(4);
+            PCNN_TRACE2(4);
 #pragma unroll 1
             for (int e = t; e < cnt; e += NT) {
                 const int p = e0 + e;
                 const llword *sp = a.slots_ll + p;
-                PollGuard guard(a.abort_flag);
+                PollGuard guard(a.abort_flag, &S.aborted);
                 float acc = 0.0f;
-                for (int k = 0; k < G; ++k) {
+                for (int k = 0; k < NC; ++k) {
                     float v;
                     unsigned g;
                     for (;;) {
@@ -623,7 +447,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
             }
         }
         __syncwarp();
-        PCNN_TRACE(5);
+        PCNN_TRACE2(5);
         cursor = ncur;
         base = nbase;
         nb = nnb;
@@ -632,21 +456,44 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         *a.cursor = cursor;
         *a.step_idx = step_idx0 + a.nsteps;
     }
+    if (CS > 1) cluster_sync_all();     // no CTA leaves while a cluster peer may still push into its shared memory
 }
 
+constexpr int PERSIST_CS = 8;            // cluster size of the dataflow kernel (1 = fallback without clusters)
+
 template <typename InT> int persist_cap(int *out) {
-    int per_sm = 0, per_sm_bar = 0;
-    cudaError_t e = cudaFuncSetAttribute(k_train_persist<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sizeof(FusedSmem<InT>));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(k_train_persist_bar<InT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<InT>));
-    if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_train_persist<InT>, NT, sizeof(FusedSmem<InT>));
-    if (e == cudaSuccess)
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_bar, k_train_persist_bar<InT>, NT, sizeof(FusedSmem<InT>));
-    if (e != cudaSuccess) return pcnn_fail_cuda(e, "persistent kernel occupancy", __FILE__, __LINE__);
-    *out = per_sm < per_sm_bar ? per_sm : per_sm_bar;
+    int m = 1 << 30;
+    const void *fns[2] = {(const void *)k_train_persist<InT, PERSIST_CS>, (const void *)k_train_persist<InT, 1>};
+    for (const void *fn : fns) {
+        int per_sm = 0;
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<InT>));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, NT, sizeof(FusedSmem<InT>));
+        if (e != cudaSuccess) return pcnn_fail_cuda(e, "persistent kernel occupancy", __FILE__, __LINE__);
+        if (per_sm < m) m = per_sm;
+    }
+    *out = m;
     return PCNN_OK;
+}
+
+// CTAs that can be co-resident when the grid is launched as clusters of PERSIST_CS (0 when they cannot be scheduled)
+template <typename InT> int cluster_cap(int sm_count) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(PERSIST_CS * sm_count));     // any multiple of the cluster size
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = sizeof(FusedSmem<InT>);
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = PERSIST_CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k_train_persist<InT, PERSIST_CS>, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n * PERSIST_CS;
 }
 
 }  // namespace
@@ -659,11 +506,33 @@ int pcnn_persist_configure(pcnn_ctx *ctx) {
     if (per_sm > FUSED_CTAS_PER_SM) per_sm = FUSED_CTAS_PER_SM;
     ctx->persist_cap = per_sm * ctx->sm_count;
     if (ctx->persist_cap > MAX_SLOTS) ctx->persist_cap = MAX_SLOTS;
+    {
+        const int u = cluster_cap<uint8_t>(ctx->sm_count), f = cluster_cap<float>(ctx->sm_count);
+        int cap = u < f ? u : f;
+        if (cap > ctx->persist_cap) cap = ctx->persist_cap;
+        ctx->persist_cluster_cap = cap - cap % PERSIST_CS;
+    }
     PCNN_CUDA(cudaMalloc((void **)&ctx->d_slots_ll, (size_t)MAX_SLOTS * NPACK * sizeof(llword)));
     PCNN_CUDA(cudaMalloc((void **)&ctx->d_params_ll, (size_t)NPACK * sizeof(llword)));
     PCNN_CUDA(cudaMemset(ctx->d_slots_ll, 0, (size_t)MAX_SLOTS * NPACK * sizeof(llword)));
     PCNN_CUDA(cudaMemset(ctx->d_params_ll, 0, (size_t)NPACK * sizeof(llword)));
     return PCNN_OK;
+}
+
+// Grid and cluster size of the dataflow kernel for a per-rank batch of B: one image per CTA while the device can hold them,
+// rounded up to whole clusters (CTAs without an image still take part in the reduction); clusters of PERSIST_CS whenever the
+// device can keep that grid co-resident, otherwise single CTAs.
+static void persist_geometry(const pcnn_ctx *ctx, int B, int *grid, int *cs) {
+    const int want = B < ctx->persist_cap ? B : ctx->persist_cap;
+    const int capc = ctx->persist_force_cluster == 1 ? 0 : ctx->persist_cluster_cap;
+    if (capc >= PERSIST_CS) {
+        int g = ((want + PERSIST_CS - 1) / PERSIST_CS) * PERSIST_CS;
+        if (g > capc) g = capc;
+        // a grid slightly smaller than the batch only means some CTAs take two images; never give up more than 1/8
+        if (g >= want || g * 8 >= want * 7) { *grid = g; *cs = PERSIST_CS; return; }
+    }
+    *grid = want;
+    *cs = 1;
 }
 
 // nsteps cursor-driven steps of batch B over split `s` in one cooperative launch.  `gate` (optional) makes the kernel wait
@@ -672,9 +541,8 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
                      float *step_err_host, int fresh) {
     PCNN_REQUIRE(ctx->persist_cap > 0, PCNN_ERR_STATE, "persistent kernel cannot be co-resident on this device");
     PCNN_REQUIRE(ctx->world == 1 || ctx->p2p_ready, PCNN_ERR_STATE, "persistent multi-GPU steps need pcnn_p2p_attach");
-    const bool barrier_variant = ctx->step_mode == PCNN_MODE_PERSISTENT_BARRIER;
     while (nsteps > 0) {
-        const int k = nsteps > 1000000 ? 1000000 : (int)nsteps;   // keeps the 32-bit barrier counter in range
+        const int k = nsteps > 1000000 ? 1000000 : (int)nsteps;   // bounds one launch (and the ids it consumes)
         // tags are unique per context lifetime; long before the 32-bit ids wrap, start over on cleared buffers
         if (ctx->ll_step_id > 0xF0000000u) {
             PCNN_CUDA(cudaMemsetAsync(ctx->d_slots_ll, 0, (size_t)MAX_SLOTS * NPACK * sizeof(llword), ctx->stream));
@@ -689,8 +557,6 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
         a.n_total = s.n;
         a.params = ctx->d_params;
         a.grads = ctx->d_grads;
-        a.slots = ctx->d_slots;
-        a.bar = ctx->d_bar;
         a.cursor = ctx->d_cursor;
         a.err_total = ctx->d_err_total;
         a.step_err = ctx->d_step_err;
@@ -707,7 +573,7 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
         a.trace = ctx->d_trace;
         a.slots_ll = ctx->d_slots_ll;
         a.params_ll = ctx->d_params_ll;
-        a.step_base = barrier_variant ? ctx->p2p_step_id : ctx->ll_step_id;
+        a.step_base = ctx->ll_step_id;
         a.xstep_base = ctx->p2p_step_id;
         // k + 1 ids per launch: the parameters published after the last step (tag base + k + 1) must never look like the
         // first step's parameters of the next launch (pcnn_set_params may have changed them in between)
@@ -723,18 +589,54 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
         fresh = 0;                                                 // a split longer than one launch continues
         a.step_err_host = step_err_host;
         if (step_err_host) step_err_host += k;
-        int grid = B < ctx->persist_cap ? B : ctx->persist_cap;
         void *args[] = {&a};
-        const void *fn;
-        if (barrier_variant) {
-            PCNN_CUDA(cudaMemsetAsync(ctx->d_bar, 0, sizeof(unsigned), ctx->stream));
-            fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist_bar<uint8_t> : (const void *)k_train_persist_bar<float>;
-        } else {
-            fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist<uint8_t> : (const void *)k_train_persist<float>;
-        }
         const size_t smem = s.pixel_type == PCNN_U8 ? sizeof(FusedSmem<uint8_t>) : sizeof(FusedSmem<float>);
-        cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NT), args, smem, ctx->stream);
-        if (e != cudaSuccess) return pcnn_fail_cuda(e, "cudaLaunchCooperativeKernel(k_train_persist)", __FILE__, __LINE__);
+        cudaError_t e;
+        {
+            int grid = 0, cs = 1;
+            persist_geometry(ctx, B, &grid, &cs);
+            const void *fn;
+            if (cs > 1)
+                fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist<uint8_t, PERSIST_CS> : (const void *)k_train_persist<float, PERSIST_CS>;
+            else
+                fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist<uint8_t, 1> : (const void *)k_train_persist<float, 1>;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid);
+            cfg.blockDim = dim3(NT);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute at[2];
+            int na = 0;
+            // co-residency of the whole grid is what the polling loops rely on: cooperative launch guarantees it
+            // (the launch fails instead of deadlocking when the grid does not fit)
+            if (!ctx->persist_no_coop) {
+                at[na].id = cudaLaunchAttributeCooperative;
+                at[na].val.cooperative = 1;
+                ++na;
+            }
+            if (cs > 1) {
+                at[na].id = cudaLaunchAttributeClusterDimension;
+                at[na].val.clusterDim.x = (unsigned)cs;
+                at[na].val.clusterDim.y = 1;
+                at[na].val.clusterDim.z = 1;
+                ++na;
+            }
+            cfg.attrs = at;
+            cfg.numAttrs = (unsigned)na;
+            e = cudaLaunchKernelExC(&cfg, fn, args);
+            if (e != cudaSuccess && cs > 1 && !ctx->persist_no_coop) {
+                // a driver that refuses cooperative + cluster launches: the grid was sized by cudaOccupancyMaxActiveClusters,
+                // so it is co-resident on an otherwise idle device; remember the choice
+                cudaGetLastError();
+                ctx->persist_no_coop = true;
+                cfg.attrs = at + 1;
+                cfg.numAttrs = 1;
+                e = cudaLaunchKernelExC(&cfg, fn, args);
+            }
+            ctx->persist_last_cluster = cs;
+            ctx->persist_last_grid = grid;
+        }
+        if (e != cudaSuccess) return pcnn_fail_cuda(e, "launch of k_train_persist", __FILE__, __LINE__);
         ctx->launches += 1;
         ctx->persist_used = true;
         nsteps -= k;
@@ -750,7 +652,8 @@ int pcnn_persist_check(pcnn_ctx *ctx) {
     if (flag) {
         cudaMemset(ctx->d_abort, 0, sizeof(int));
         pcnn_set_error("persistent training kernel aborted: %s wait exceeded its cycle budget",
-                       flag == 2 ? "peer-GPU exchange" : (flag == 3 ? "host-streamed chunk" : "slot / parameter"));
+                       flag == 2 ? "peer-GPU exchange" : (flag == 3 ? "host-streamed chunk" :
+                       (flag == 4 ? "launched without its cluster dimension; no" : "slot / parameter")));
         return PCNN_ERR_STATE;
     }
     return PCNN_OK;
@@ -828,7 +731,7 @@ extern "C" int pcnn_p2p_detach(pcnn_ctx *ctx) {
 extern "C" int pcnn_persist_trace(pcnn_ctx *ctx, long long *host_out, int cap_steps) {
     PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_persist_trace: ctx is NULL");
     pcnn_device_guard g(ctx->device);
-    const size_t bytes = (size_t)PCNN_TRACE_STEPS * 6 * sizeof(long long);
+    const size_t bytes = ((size_t)PCNN_TRACE_STEPS * 6 + (size_t)MAX_SLOTS * 8) * sizeof(long long);
     if (!host_out) {
         if (!ctx->d_trace) PCNN_CUDA(cudaMalloc((void **)&ctx->d_trace, bytes));
         PCNN_CUDA(cudaMemsetAsync(ctx->d_trace, 0, bytes, ctx->stream));
@@ -841,9 +744,40 @@ extern "C" int pcnn_persist_trace(pcnn_ctx *ctx, long long *host_out, int cap_st
     return PCNN_OK;
 }
 
+// per-CTA stamps of step PCNN_TRACE_STEPS / 2 of the traced launch: rows of 8 (6 phase stamps, SM id, spare)
+extern "C" int pcnn_persist_trace_ctas(pcnn_ctx *ctx, long long *host_out, int cap_ctas) {
+    PCNN_REQUIRE(ctx && host_out, PCNN_ERR_ARG, "pcnn_persist_trace_ctas: NULL argument");
+    PCNN_REQUIRE(ctx->d_trace, PCNN_ERR_STATE, "pcnn_persist_trace_ctas: tracing was not enabled");
+    pcnn_device_guard g(ctx->device);
+    PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int n = cap_ctas < MAX_SLOTS ? cap_ctas : MAX_SLOTS;
+    PCNN_CUDA(cudaMemcpy(host_out, ctx->d_trace + PCNN_TRACE_STEPS * 6, (size_t)n * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_persist_info(pcnn_ctx *ctx, int *out6) {
+    PCNN_REQUIRE(ctx && out6, PCNN_ERR_ARG, "pcnn_persist_info: NULL argument");
+    out6[0] = ctx->persist_last_grid;
+    out6[1] = ctx->persist_last_cluster;
+    out6[2] = ctx->persist_cap;
+    out6[3] = ctx->persist_cluster_cap;
+    out6[4] = PERSIST_CS;
+    out6[5] = ctx->persist_no_coop ? 0 : 1;
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_persist_tune(pcnn_ctx *ctx, int max_cluster) {
+    PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_persist_tune: ctx is NULL");
+    PCNN_REQUIRE(max_cluster >= 0 && max_cluster <= 2, PCNN_ERR_ARG,
+                 "pcnn_persist_tune: 0 (automatic), 1 (no clusters) or 2 (clusters without the cooperative attribute)");
+    ctx->persist_force_cluster = max_cluster == 1 ? 1 : 0;
+    if (max_cluster == 2) ctx->persist_no_coop = true;
+    return PCNN_OK;
+}
+
 extern "C" int pcnn_set_step_mode(pcnn_ctx *ctx, int mode) {
     PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_set_step_mode: ctx is NULL");
-    PCNN_REQUIRE(mode >= PCNN_MODE_AUTO && mode <= PCNN_MODE_PERSISTENT_BARRIER, PCNN_ERR_ARG, "pcnn_set_step_mode: bad mode %d", mode);
+    PCNN_REQUIRE(mode >= PCNN_MODE_AUTO && mode <= PCNN_MODE_PERSISTENT, PCNN_ERR_ARG, "pcnn_set_step_mode: bad mode %d", mode);
     ctx->step_mode = mode;
     return PCNN_OK;
 }

@@ -327,6 +327,20 @@ class Engine:
     def set_step_mode(self, mode):
         self._call("pcnn_set_step_mode", int(mode))
 
+    def persist_trace_ctas(self, ctas):
+        out = np.zeros((int(ctas), 8), np.int64)
+        self._call("pcnn_persist_trace_ctas", out.ctypes.data, int(ctas))
+        return out
+
+    def persist_info(self):
+        out = np.zeros(6, np.int32)
+        self._call("pcnn_persist_info", out.ctypes.data)
+        return {"grid": int(out[0]), "cluster": int(out[1]), "cta_capacity": int(out[2]), "cta_capacity_clustered": int(out[3]),
+                "cluster_size_used_when_possible": int(out[4]), "cooperative": bool(out[5])}
+
+    def persist_tune(self, max_cluster=0):
+        self._call("pcnn_persist_tune", int(max_cluster))
+
     def persist_trace_arm(self):
         self._call("pcnn_persist_trace", None, 0)
 

@@ -11,6 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liblenet_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_seq.so")
+REF_NATIVE_SO = os.path.join(ROOT, "oracle", "_ref", "libref_seq_native.so")   # -O3 -march=x86-64-v3: timing only
 REF_DATA = os.path.join(ROOT, "oracle", "_ref", "data")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -52,6 +53,7 @@ def i32p(a):
 
 _oracle = None
 _ref = None
+_ref_native = None
 
 
 def oracle():
@@ -89,9 +91,17 @@ def oracle():
     return _oracle
 
 
-def reference():
-    """The unmodified reference, or None when oracle/_ref was not built (no /root/reference at build time)."""
-    global _ref
+def reference(native=False):
+    """The unmodified reference, or None when oracle/_ref was not built (no /root/reference at build time).
+    native=True: the same sources built -O3 with FMA contraction (bench.py's best-CPU timing; NOT a parity checker)."""
+    global _ref, _ref_native
+    if native:
+        if _ref_native is None and os.path.exists(REF_NATIVE_SO):
+            L = C.CDLL(REF_NATIVE_SO)
+            L.ref_learn_loop_u8.restype = C.c_float
+            L.ref_learn_loop_u8.argtypes = [_u8, _u8, C.c_long, _d]
+            _ref_native = L
+        return _ref_native
     if _ref is None:
         if not os.path.exists(REF_SO):
             return None
