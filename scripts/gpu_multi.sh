@@ -6,12 +6,11 @@ N=${N:-2}
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi -L | head -8
 nvidia-smi topo -m 2>/dev/null | head -12 > $OUT/topo_$N.txt
-for MODE in p2p nccl; do
-  echo "== parity N=$N mode=$MODE"
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) \
-      tests/mgpu_worker.py --mode $MODE 2>&1 | grep -E "MGPU|rel-L2|Error|error" | head -5
-done
-for MODE in persistent graph; do
+echo "== parity (pytest, world = all visible GPUs, batch 64 and 1024)"
+rm -f $OUT/mgpu_parity_n$N.log
+PCNN_MGPU_LOG_DIR=$PWD/$OUT timeout 900 python -m pytest tests/test_persist_gpu.py -m gpu -q -x -p no:cacheprovider -k data_parallel 2>&1 | tail -5
+cat $OUT/mgpu_parity_n$N.log
+for MODE in ${MODES:-persistent graph}; do
   echo "== bench N=$N mode=$MODE"
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700 + RANDOM % 200)) \
       bench.py --gpus $N --steps ${STEPS:-2000} --warmup 100 --mode $MODE --no-cpu-baseline > $OUT/bench_n${N}_$MODE.json 2> $OUT/bench_n${N}_$MODE.err
@@ -19,7 +18,7 @@ for MODE in persistent graph; do
 import json
 try:
     d=json.loads(open("$OUT/bench_n${N}_$MODE.json").read().strip().splitlines()[-1])
-    print({k:d[k] for k in ("value","n_gpus","ms_per_step")}, "e2e", d["e2e"]["value"], d["config"]["step_mode"])
+    print({k:d[k] for k in ("value","n_gpus","ms_per_step")}, "e2e", d["e2e"]["value"], d["config"]["step_mode"], "parity", d.get("parity"), "b1024", d.get("batch1024"))
 except Exception as e:
     print("no json", e); print(open("$OUT/bench_n${N}_$MODE.err").read()[-1500:])
 PY
