@@ -587,6 +587,10 @@ static int ensure_host_stream(pcnn_ctx *ctx, size_t image_bytes, long labels, lo
         ctx->hs_ready_cap = cap;
     }
     if (!ctx->h_hs_tag) PCNN_CUDA(cudaMallocHost((void **)&ctx->h_hs_tag, sizeof(unsigned)));
+    if (!ctx->h_hs_done) {
+        PCNN_CUDA(cudaMallocHost((void **)&ctx->h_hs_done, 2 * sizeof(double)));
+        ctx->h_hs_done[0] = ctx->h_hs_done[1] = 0.0;
+    }
     return PCNN_OK;
 }
 
@@ -636,8 +640,16 @@ static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel
             tmp.rank_local = true;
             const long steps = (sn + B - 1) / B;
             const int fresh = 1 | (off == 0 ? 2 : 0);
+            const bool last = off + sn >= n && ep + 1 == epochs;        // the launch whose completion ends the call
+            unsigned done_tag = 0;
+            if (last) {
+                done_tag = ++ctx->hs_serial;
+                if (done_tag == 0) done_tag = ++ctx->hs_serial;
+            }
             if (ep > 0 && resident_after_first) {
-                if ((rc = pcnn_persist_run(ctx, tmp, B, steps, nullptr, ctx->h_step_err + steps_done, fresh))) return rc;
+                if ((rc = pcnn_persist_run(ctx, tmp, B, steps, nullptr, ctx->h_step_err + steps_done, fresh, last ? ctx->h_hs_done : nullptr,
+                                           done_tag)))
+                    return rc;
             } else {
                 pcnn_persist_gate gate;
                 gate.flags = ctx->d_hs_ready;
@@ -646,8 +658,12 @@ static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel
                 gate.first_samples = first < sn ? first : sn;
                 gate.chunk_samples = chunk;
                 *ctx->h_hs_tag = gate.tag;   // the previous user of this word has been synchronised with (end of every launch)
+                // The kernel goes first: it sets itself up while the host enqueues the copies, and waits on the flag of a
+                // sample's chunk before it touches the sample.
+                if ((rc = pcnn_persist_run(ctx, tmp, B, steps, &gate, ctx->h_step_err + steps_done, fresh, last ? ctx->h_hs_done : nullptr,
+                                           done_tag)))
+                    return rc;
                 PCNN_CUDA(cudaMemcpyAsync(ctx->d_hs_labels, host_labels + off, (size_t)sn, cudaMemcpyHostToDevice, ctx->copy_stream));
-                bool launched = false;
                 long k = 0;
                 for (long co = 0; co < sn; ++k) {
                     const long cs0 = k == 0 ? gate.first_samples : chunk;
@@ -656,25 +672,37 @@ static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel
                                               (size_t)cs * img_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
                     PCNN_CUDA(cudaMemcpyAsync(ctx->d_hs_ready + k, ctx->h_hs_tag, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->copy_stream));
                     co += cs;
-                    if (!launched) {         // the kernel starts as soon as chunk 0 is on its way
-                        if ((rc = pcnn_persist_run(ctx, tmp, B, steps, &gate, ctx->h_step_err + steps_done, fresh))) return rc;
-                        launched = true;
-                    }
                 }
             }
             steps_done += steps;
-            if (off + sn < n || !(ep + 1 < epochs && resident_after_first)) {
-                // the staging buffer is about to be refilled (or the call ends): wait for the kernel
+            if (last) {
+                // Results (per-step sums, total, completion tag) arrive in pinned host memory straight from the kernel: poll
+                // the tag instead of paying a stream synchronisation; the stream is queried now and then so that an aborted
+                // or failed launch cannot hang the host.
+                volatile unsigned *tagp = reinterpret_cast<volatile unsigned *>(ctx->h_hs_done + 1);
+                bool seen = false;
+                for (unsigned long spins = 0;; ++spins) {
+                    if (*tagp == done_tag) { seen = true; break; }
+                    if ((spins & 4095) == 4095) {
+                        const cudaError_t q = cudaStreamQuery(ctx->stream);
+                        if (q == cudaSuccess) { seen = (*tagp == done_tag); break; }
+                        if (q != cudaErrorNotReady) return pcnn_fail_cuda(q, "persistent training kernel", __FILE__, __LINE__);
+                    }
+                }
+                if (!seen) {
+                    PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+                    if ((rc = pcnn_persist_check(ctx))) return rc;
+                    PCNN_REQUIRE(*tagp == done_tag, PCNN_ERR_STATE, "pcnn_learn_host: the training kernel ended without reporting completion");
+                }
+                err = ctx->h_hs_done[0];
+            } else if (off + sn < n || !resident_after_first) {
+                // the staging buffer is about to be refilled: wait for the kernel
                 PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
                 if ((rc = pcnn_persist_check(ctx))) return rc;
             }
         }
         ctx->step_err_count = steps_done;
     }
-    PCNN_CUDA(cudaMemcpyAsync(ctx->h_scalar, ctx->d_err_total, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
-    if ((rc = pcnn_persist_check(ctx))) return rc;
-    err = *reinterpret_cast<double *>(ctx->h_scalar);
     if (mean_err_out) *mean_err_out = (float)(err / ((double)n * ctx->world));   // err is the all-reduced sum
     return PCNN_OK;
 }

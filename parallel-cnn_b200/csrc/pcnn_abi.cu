@@ -113,6 +113,7 @@ extern "C" int pcnn_destroy(pcnn_ctx *ctx) {
     if (ctx->d_hs_labels) cudaFree(ctx->d_hs_labels);
     if (ctx->d_hs_ready) cudaFree(ctx->d_hs_ready);
     if (ctx->h_hs_tag) cudaFreeHost(ctx->h_hs_tag);
+    if (ctx->h_hs_done) cudaFreeHost(ctx->h_hs_done);
     if (ctx->d_slots_ll) cudaFree(ctx->d_slots_ll);
     if (ctx->d_params_ll) cudaFree(ctx->d_params_ll);
     if (ctx->d_abort) cudaFree(ctx->d_abort);

@@ -96,6 +96,7 @@ struct pcnn_ctx {
     size_t hs_image_bytes = 0;
     long hs_label_cap = 0, hs_ready_cap = 0;
     unsigned hs_serial = 0;
+    double *h_hs_done = nullptr;            // pinned {double error sum, unsigned tag} written by the kernel after its last step
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
 
@@ -181,7 +182,7 @@ struct pcnn_persist_gate {
 };
 // fresh bit 0: start at sample 0 / step 0 (no device-side counter read); bit 1: the error sum restarts at 0
 int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nsteps, const pcnn_persist_gate *gate = nullptr,
-                     float *step_err_host = nullptr, int fresh = 0);
+                     float *step_err_host = nullptr, int fresh = 0, double *done_host = nullptr, unsigned done_tag = 0);
 int pcnn_persist_check(pcnn_ctx *ctx);
 // comm.cu
 int pcnn_comm_allreduce_packed(pcnn_ctx *ctx);

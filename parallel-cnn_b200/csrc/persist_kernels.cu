@@ -37,6 +37,8 @@ struct PersistArgs {
     long long ready_chunk;    // samples in every later chunk
     int fresh;                // bit 0: start at sample 0 / step 0 instead of the device-side counters; bit 1: err_total = 0
     float *step_err_host;     // optional mapped pinned array [nsteps]: per-step error sums written straight to the host
+    double *done_host;        // optional mapped pinned {double error sum, unsigned tag}: written after the LAST step, so the
+    unsigned done_tag;        //   host can return as soon as the results are there instead of waiting for the stream
     long long *trace;         // optional [PCNN_TRACE_STEPS][6] globaltimer stamps written by CTA 0 (pcnn_persist_trace)
 };
 
@@ -382,9 +384,16 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
                 w = updated_entry(w_old, p, g, step);
                 a.params[p] = w;
             } else {
-                *a.err_total = (s == 0 && (a.fresh & 2)) ? (double)g : *a.err_total + (double)g;
+                const double tot = (s == 0 && (a.fresh & 2)) ? (double)g : *a.err_total + (double)g;
+                *a.err_total = tot;
                 a.step_err[(step_idx0 + s) & (STEP_ERR_CAP - 1)] = g;
                 if (a.step_err_host) a.step_err_host[s] = g;
+                // an aborted launch never reports completion: the host then falls back to a stream synchronisation + abort check
+                if (a.done_host && s + 1 == a.nsteps && *(volatile int *)a.abort_flag == 0) {   // same thread as the per-step stores
+                    *(volatile double *)a.done_host = tot;
+                    __threadfence_system();
+                    *(volatile unsigned *)(a.done_host + 1) = a.done_tag;
+                }
             }
             ll_store(a.params_ll + p, w, tag + 1u);
             return w;
@@ -538,7 +547,7 @@ static void persist_geometry(const pcnn_ctx *ctx, int B, int *grid, int *cs) {
 // nsteps cursor-driven steps of batch B over split `s` in one cooperative launch.  `gate` (optional) makes the kernel wait
 // for host-streamed chunks; `step_err_host` (optional, mapped pinned) receives every step's error sum.
 int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nsteps, const pcnn_persist_gate *gate,
-                     float *step_err_host, int fresh) {
+                     float *step_err_host, int fresh, double *done_host, unsigned done_tag) {
     PCNN_REQUIRE(ctx->persist_cap > 0, PCNN_ERR_STATE, "persistent kernel cannot be co-resident on this device");
     PCNN_REQUIRE(ctx->world == 1 || ctx->p2p_ready, PCNN_ERR_STATE, "persistent multi-GPU steps need pcnn_p2p_attach");
     while (nsteps > 0) {
@@ -589,6 +598,10 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
         fresh = 0;                                                 // a split longer than one launch continues
         a.step_err_host = step_err_host;
         if (step_err_host) step_err_host += k;
+        if (nsteps == k) {            // the last launch of this run reports completion
+            a.done_host = done_host;
+            a.done_tag = done_tag;
+        }
         void *args[] = {&a};
         const size_t smem = s.pixel_type == PCNN_U8 ? sizeof(FusedSmem<uint8_t>) : sizeof(FusedSmem<float>);
         cudaError_t e;
