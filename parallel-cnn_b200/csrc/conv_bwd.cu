@@ -25,11 +25,6 @@ void pcnn_conv_wgrad_rows_info(int H, int W, int C, int K, int R, int S, int *ou
 
 namespace {
 
-bool force_fma() {
-    const char *v = getenv("PCNN_CONV_BWD");
-    return v && v[0] == 'f';
-}
-
 constexpr int WG_THREADS = 256;
 constexpr int WG_MAXO = 20;           // outputs per thread: K*R*S*C <= 5120
 
@@ -136,8 +131,13 @@ extern "C" int pcnn_conv_wgrad(pcnn_ctx *ctx, const void *x_bf16, const void *dy
     ConvShape s;
     int rc = check_shape("pcnn_conv_wgrad", N, H, W, C, K, R, S, row_pitch, image_rows, &s);
     if (rc) return rc;
-    if (!force_fma() && pcnn_conv_wgrad_rows_ok(N, H, W, C, K, R, S, s.row_pitch, x_bf16, dy_bf16))
+    if (ctx->conv_bwd_path == PCNN_CONV_BWD_TENSOR) {
+        PCNN_REQUIRE(pcnn_conv_wgrad_rows_ok(N, H, W, C, K, R, S, s.row_pitch, x_bf16, dy_bf16), PCNN_ERR_ARG,
+                     "pcnn_conv_wgrad: no tensor-core kernel for C = %d, K = %d, %dx%d taps (needs K = 64/128/192/256, (RB + R - 1) * S * C <= 64, "
+                     "16-byte aligned operands); the FMA-pipe reference kernels (~1 %% of the HBM roofline) must be selected explicitly with "
+                     "pcnn_conv_bwd_select(ctx, PCNN_CONV_BWD_REFERENCE)", C, K, R, S);
         return pcnn_conv_wgrad_rows(ctx, x_bf16, dy_bf16, dw_f32, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
+    }
     const int nout = K * R * S * C;
     PCNN_REQUIRE(nout <= WG_THREADS * WG_MAXO, PCNN_ERR_ARG, "pcnn_conv_wgrad: K*R*S*C = %d exceeds %d", nout, WG_THREADS * WG_MAXO);
     pcnn_device_guard g(ctx->device);
@@ -159,8 +159,13 @@ extern "C" int pcnn_conv_dgrad(pcnn_ctx *ctx, const void *dy_bf16, const float *
     ConvShape s;
     int rc = check_shape("pcnn_conv_dgrad", N, H, W, C, K, R, S, row_pitch, image_rows, &s);
     if (rc) return rc;
-    if (!force_fma() && pcnn_conv_dgrad_rows_ok(N, H, W, C, K, R, S, dy_bf16))
+    if (ctx->conv_bwd_path == PCNN_CONV_BWD_TENSOR) {
+        PCNN_REQUIRE(pcnn_conv_dgrad_rows_ok(N, H, W, C, K, R, S, dy_bf16), PCNN_ERR_ARG,
+                     "pcnn_conv_dgrad: no tensor-core kernel for C = %d, K = %d, %dx%d taps (needs K = 64/128/192/256 and 3x3 taps with C in "
+                     "{1,2,3,4,8}, 5x5 with C in {1,3} or 7x7 with C = 1); the FMA-pipe reference kernels (~1 %% of the HBM roofline) must be "
+                     "selected explicitly with pcnn_conv_bwd_select(ctx, PCNN_CONV_BWD_REFERENCE)", C, K, R, S);
         return pcnn_conv_dgrad_rows(ctx, dy_bf16, filt_f32_dev, dx_bf16, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
+    }
     pcnn_device_guard g(ctx->device);
     const long total = (long)N * H * W * C;
     long blocks = (total + 255) / 256;
@@ -168,6 +173,13 @@ extern "C" int pcnn_conv_dgrad(pcnn_ctx *ctx, const void *dy_bf16, const float *
     k_conv_dgrad<<<(int)blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const __nv_bfloat16 *>(dy_bf16), filt_f32_dev,
                                                       reinterpret_cast<__nv_bfloat16 *>(dx_bf16), s);
     PCNN_CHECK_LAUNCH(ctx);
+    return PCNN_OK;
+}
+
+extern "C" int pcnn_conv_bwd_select(pcnn_ctx *ctx, int path) {
+    PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_conv_bwd_select: ctx is NULL");
+    PCNN_REQUIRE(path == PCNN_CONV_BWD_TENSOR || path == PCNN_CONV_BWD_REFERENCE, PCNN_ERR_ARG, "pcnn_conv_bwd_select: bad path %d", path);
+    ctx->conv_bwd_path = path;
     return PCNN_OK;
 }
 

@@ -78,14 +78,16 @@ struct RowWalk {
     }
 };
 
-template <int R, int S, int C>
+template <int R, int S, int C, int KHC>
 __global__ void __launch_bounds__(D2_THREADS, 1)
 k_conv_tc_dgrad_rows(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_b, const Dgrad2Params p) {
     constexpr int SC = S * C, SCP = (SC + 3) / 4 * 4, NW = (R * SCP + 15) / 16 * 16;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     constexpr int BMAT = NW * 128;
-    const int KH = p.KH, STAGE = KH * D2_HALF_BYTES;
+    // KHC > 0: the channel-group count is a compile-time constant (64 filters: KHC = 1 keeps the single issuing thread's loop
+    // free of the group bookkeeping -- the runtime loop cost 146 -> 187 us at config 5); KHC = 0: p.KH groups at run time
+    const int KH = KHC > 0 ? KHC : p.KH, STAGE = KH * D2_HALF_BYTES;
     unsigned char *bvar = base;                                         // [R][KH][NW][64] bf16, SWIZZLE_128B
     unsigned char *astage = base + (size_t)R * KH * BMAT;               // [stages][KH][4][32][64] bf16, SWIZZLE_128B
     Dgrad2Ctl &B = *reinterpret_cast<Dgrad2Ctl *>(astage + (size_t)p.stages * STAGE);
@@ -275,16 +277,20 @@ Geometry geometry(int R, int S, int C) {
     return g;
 }
 
-template <int R, int S, int C>
-int launch_rows(pcnn_ctx *ctx, const CUtensorMap &map_dy, const CUtensorMap &map_b, const Dgrad2Params &p, int grid, size_t smem) {
+template <int R, int S, int C, int KHC>
+int launch_rows_k(pcnn_ctx *ctx, const CUtensorMap &map_dy, const CUtensorMap &map_b, const Dgrad2Params &p, int grid, size_t smem) {
     static bool configured[64] = {};        // function attributes are per device
     if (!configured[ctx->device & 63]) {
-        PCNN_CUDA(cudaFuncSetAttribute(k_conv_tc_dgrad_rows<R, S, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BUDGET + 2048));
+        PCNN_CUDA(cudaFuncSetAttribute(k_conv_tc_dgrad_rows<R, S, C, KHC>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BUDGET + 2048));
         configured[ctx->device & 63] = true;
     }
-    k_conv_tc_dgrad_rows<R, S, C><<<grid, D2_THREADS, smem, ctx->stream>>>(map_dy, map_b, p);
+    k_conv_tc_dgrad_rows<R, S, C, KHC><<<grid, D2_THREADS, smem, ctx->stream>>>(map_dy, map_b, p);
     PCNN_CHECK_LAUNCH(ctx);
     return PCNN_OK;
+}
+template <int R, int S, int C>
+int launch_rows(pcnn_ctx *ctx, const CUtensorMap &map_dy, const CUtensorMap &map_b, const Dgrad2Params &p, int grid, size_t smem) {
+    return p.KH == 1 ? launch_rows_k<R, S, C, 1>(ctx, map_dy, map_b, p, grid, smem) : launch_rows_k<R, S, C, 0>(ctx, map_dy, map_b, p, grid, smem);
 }
 
 }  // namespace
@@ -333,8 +339,6 @@ int pcnn_conv_dgrad_rows(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f
     const size_t fixed = (size_t)R * p.KH * g.nw * 128 + sizeof(Dgrad2Ctl) + 1024;
     int st = (int)(((size_t)D2_SMEM_BUDGET - fixed) / stage_bytes);
     p.stages = st > D2_MAX_STAGES ? D2_MAX_STAGES : st;
-    const char *es = getenv("PCNN_DGRAD_STAGES");
-    if (es && atoi(es) >= 2 && atoi(es) < p.stages) p.stages = atoi(es);
     PCNN_REQUIRE(p.stages >= 2, PCNN_ERR_ARG, "pcnn_conv_dgrad: filter variants leave no room for two stages");
     const size_t smem = fixed + (size_t)p.stages * stage_bytes;
 

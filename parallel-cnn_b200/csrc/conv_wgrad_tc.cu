@@ -264,15 +264,10 @@ __global__ void __launch_bounds__(256) k_conv_tc_wgrad_rows_reduce(const float *
 
 struct Plan { int RB, PC, stages; size_t stage_bytes, smem; bool ok; };
 
-int env_i(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
-
 // Tile shape: dy rows per tile RB (N = RB * 64) and pixels per tile PC.  Measured at config 5 (profiles/r01_README.md): what
 // matters is that the tiles cover the [P x Q] plane with little padding (PC = 112 covers Q = 222 in two chunks: 139-147 us;
 // PC = 80 in three: 149-244 us) and that at least three stages fit; RB = 3 (139 us) ~ RB = 2 (141 us) < RB = 4 (147 us, two
-// stages).  PCNN_WGRAD_RB / PCNN_WGRAD_PC override the choice for sweeps.
+// stages).
 Plan plan_for(int P, int Q, int C, int R, int S, int KH) {
     Plan pl;
     memset(&pl, 0, sizeof(pl));
@@ -280,9 +275,7 @@ Plan plan_for(int P, int Q, int C, int R, int S, int KH) {
     double best = -1.0;
     for (int RB = 4; RB >= 1; --RB) {
         if ((RB + R - 1) * SC > 64 || RB * KH * 64 > 256) continue;
-        if (env_i("PCNN_WGRAD_RB", 0) > 0 && RB != env_i("PCNN_WGRAD_RB", 0)) continue;
         for (int PC = 128; PC >= 32; PC -= 16) {
-            if (env_i("PCNN_WGRAD_PC", 0) > 0 && PC != env_i("PCNN_WGRAD_PC", 0)) continue;
             const int units = (((RB + R - 1) * SC + 7) / 8) * 8 * (PC / 8);
             if (units > W2_ITEMS * 32 * W2_BUILD_WARPS) continue;
             const size_t xseg = (size_t)(((PC + S) * C * 2 + 127) / 128 * 128);

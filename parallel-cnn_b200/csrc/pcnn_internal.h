@@ -130,6 +130,8 @@ struct pcnn_ctx {
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
 
+    int conv_bwd_path = PCNN_CONV_BWD_TENSOR;   // pcnn_conv_bwd_select
+
     long launches = 0;
 };
 

@@ -356,6 +356,10 @@ class Engine:
     def maxpool_bwd(self, dout, argmax, din, planes, H, W, k):
         self._call("pcnn_maxpool_bwd", _p(dout), _p(argmax), _p(din), int(planes), int(H), int(W), int(k))
 
+    def conv_bwd_select(self, reference=False):
+        """reference=True: the FMA-pipe reference kernels for every shape (explicit opt-in); False: tensor cores only"""
+        self._call("pcnn_conv_bwd_select", 1 if reference else 0)
+
     def conv_wgrad(self, x_bf16, dy_bf16, dw_f32, N, H, W, Cin, K, R, S, row_pitch=0, image_rows=0):
         self._call("pcnn_conv_wgrad", _p(x_bf16), _p(dy_bf16), _p(dw_f32), N, H, W, Cin, K, R, S, int(row_pitch), int(image_rows))
 

@@ -132,15 +132,25 @@ def test_conv_wgrad_and_dgrad_vs_oracle(eng, pkg, shape):
     O.oracle().orc_conv_dgrad_nhwc(O.fp(dy.reshape(-1)), O.fp(f.reshape(-1)), O.fp(dx_ref.reshape(-1)), N, H, W, C, K, R, S)
     dxb, dyb = eng.to_device(pkg.f32_to_bf16_bits(x)), eng.to_device(pkg.f32_to_bf16_bits(dy))
     dw = eng.array((K, R, S, C))
-    eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
-    got_w = dw.to_host()
-    assert np.linalg.norm((got_w - dw_ref).astype(np.float64)) / np.linalg.norm(dw_ref.astype(np.float64)) <= 1e-5
-    eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
-    assert np.array_equal(dw.to_host().view(np.uint32), got_w.view(np.uint32))                                  # deterministic
     dxo = eng.array((N, H, W, C), np.uint16)
-    eng.conv_dgrad(dyb, eng.to_device(f), dxo, N, H, W, C, K, R, S)
-    got_x = pkg.bf16_bits_to_f32(dxo.to_host())
-    assert np.all(np.abs(got_x - dx_ref) <= 2.0 ** -8 * np.abs(dx_ref) + 1e-3)
+    if K % 64:
+        # default path = tensor cores only: a shape they cannot take is an error, never a silent detour to the slow kernels
+        with pytest.raises(pkg.PcnnError, match="pcnn_conv_bwd_select"):
+            eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
+        with pytest.raises(pkg.PcnnError, match="pcnn_conv_bwd_select"):
+            eng.conv_dgrad(dyb, eng.to_device(f), dxo, N, H, W, C, K, R, S)
+    eng.conv_bwd_select(reference=True)                     # the FMA-pipe reference kernels take every shape
+    try:
+        eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
+        got_w = dw.to_host()
+        assert np.linalg.norm((got_w - dw_ref).astype(np.float64)) / np.linalg.norm(dw_ref.astype(np.float64)) <= 1e-5
+        eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
+        assert np.array_equal(dw.to_host().view(np.uint32), got_w.view(np.uint32))                              # deterministic
+        eng.conv_dgrad(dyb, eng.to_device(f), dxo, N, H, W, C, K, R, S)
+        got_x = pkg.bf16_bits_to_f32(dxo.to_host())
+        assert np.all(np.abs(got_x - dx_ref) <= 2.0 ** -8 * np.abs(dx_ref) + 1e-3)
+    finally:
+        eng.conv_bwd_select(reference=False)
 
 
 def test_lenet_wgrad_matches_reference_bp_weight_c1(eng, pkg, golden):
@@ -152,8 +162,12 @@ def test_lenet_wgrad_matches_reference_bp_weight_c1(eng, pkg, golden):
     dpre = b[slice(*O.BACK_OFF["c1_dpre"])].reshape(6, 24, 24).transpose(1, 2, 0)           # -> [P][Q][K]
     dw_ref = b[slice(*O.BACK_OFF["g"])][0:150].reshape(6, 5, 5, 1)
     dw = eng.array((6, 5, 5, 1))
-    eng.conv_wgrad(eng.to_device(pkg.f32_to_bf16_bits(img.reshape(1, 28, 28, 1))), eng.to_device(pkg.f32_to_bf16_bits(dpre)), dw,
-                   1, 28, 28, 1, 6, 5, 5)
+    eng.conv_bwd_select(reference=True)                     # 6 filters: no tensor-core kernel
+    try:
+        eng.conv_wgrad(eng.to_device(pkg.f32_to_bf16_bits(img.reshape(1, 28, 28, 1))), eng.to_device(pkg.f32_to_bf16_bits(dpre)), dw,
+                       1, 28, 28, 1, 6, 5, 5)
+    finally:
+        eng.conv_bwd_select(reference=False)
     got = dw.to_host() / 576.0
     assert np.linalg.norm(got - dw_ref) / np.linalg.norm(dw_ref) <= 1e-2                                       # bf16 operands
 
@@ -166,16 +180,16 @@ BWD_TC_SHAPES = [(1, 224, 224, 3, 64, 3, 3),      # config 5
                  (1, 19, 24, 4, 64, 3, 3),        # C = 4
                  (2, 20, 40, 3, 128, 3, 3),       # 128 filters: two 64-filter groups per dy row
                  (1, 12, 24, 1, 256, 3, 3),       # 256 filters: four groups, one dy row per weight-gradient tile
-                 (1, 20, 40, 3, 64, 5, 5),        # 5x5x3: input gradient on the tensor cores, weight gradient falls back (75 Hankel rows)
+                 (1, 20, 40, 3, 64, 5, 5),        # 5x5x3: input gradient on the tensor cores, weight gradient has no tensor-core kernel (75 Hankel rows): refused
                  (1, 16, 24, 2, 64, 3, 3),        # C = 2
-                 (1, 12, 24, 8, 64, 3, 3),        # C = 8: weight gradient falls back
+                 (1, 12, 24, 8, 64, 3, 3),        # C = 8: no tensor-core weight gradient (refused)
                  (1, 20, 40, 1, 64, 7, 7)]        # 7x7 taps: lane quarters overlap by 6 pixels, 6 replayed rows
 
 
 @pytest.mark.parametrize("shape", BWD_TC_SHAPES)
-def test_tensor_core_wgrad_and_dgrad_vs_oracle_and_fma_path(eng, pkg, shape, monkeypatch):
+def test_tensor_core_wgrad_and_dgrad_vs_oracle_and_fma_path(eng, pkg, shape):
     """The tcgen05 backward kernels (csrc/conv_wgrad_tc.cu, csrc/conv_dgrad_tc.cu; 64 filters) against the oracle on the same bf16-rounded operands, and
-    against the FMA-pipe kernels of csrc/conv_bwd.cu (PCNN_CONV_BWD=fma).  fp32 accumulation everywhere:
+    against the FMA-pipe kernels of csrc/conv_bwd.cu (pcnn_conv_bwd_select).  fp32 accumulation everywhere:
     wgrad rel-L2 <= 1e-5 vs the oracle; dgrad |d| <= 2^-8 |ref| + 1e-3 (one bf16 rounding of the result)."""
     N, H, W, C, K, R, S = shape
     rng = np.random.default_rng(sum(shape) + 1)
@@ -189,26 +203,37 @@ def test_tensor_core_wgrad_and_dgrad_vs_oracle_and_fma_path(eng, pkg, shape, mon
     O.oracle().orc_conv_dgrad_nhwc(O.fp(dy.reshape(-1)), O.fp(f.reshape(-1)), O.fp(dx_ref.reshape(-1)), N, H, W, C, K, R, S)
     dxb, dyb, fd = eng.to_device(pkg.f32_to_bf16_bits(x)), eng.to_device(pkg.f32_to_bf16_bits(dy)), eng.to_device(f)
     res = {}
-    for path in ("tc", "fma"):
-        if path == "fma":
-            monkeypatch.setenv("PCNN_CONV_BWD", "fma")
-        else:
-            monkeypatch.delenv("PCNN_CONV_BWD", raising=False)
-        launches0 = eng.launch_count()
-        dw = eng.array((K, R, S, C))
-        eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
-        got_w = dw.to_host()
-        assert np.linalg.norm((got_w - dw_ref).astype(np.float64)) / np.linalg.norm(dw_ref.astype(np.float64)) <= 1e-5, path
-        eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
-        assert np.array_equal(dw.to_host().view(np.uint32), got_w.view(np.uint32)), path                       # deterministic
-        dxo = eng.array((N, H, W, C), np.uint16)
-        eng.conv_dgrad(dyb, fd, dxo, N, H, W, C, K, R, S)
-        got_x = pkg.bf16_bits_to_f32(dxo.to_host())
-        assert np.all(np.abs(got_x - dx_ref) <= 2.0 ** -8 * np.abs(dx_ref) + 1e-3), path
-        res[path] = (got_w, got_x, eng.launch_count() - launches0)
+    import ctypes as C_
+    info = (C_.c_int * 9)()
+    assert pkg.lib().pcnn_conv_bwd_plan_info(N, H, W, C, K, R, S, info) == 0
+    wgrad_tc, dgrad_tc = bool(info[0]), bool(info[4])
+    assert dgrad_tc                                          # every shape of this list has a tensor-core input gradient
+    try:
+        for path in ("tc", "fma"):
+            eng.conv_bwd_select(reference=(path == "fma"))
+            launches0 = eng.launch_count()
+            dw = eng.array((K, R, S, C))
+            got_w = None
+            if path == "fma" or wgrad_tc:
+                eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
+                got_w = dw.to_host()
+                assert np.linalg.norm((got_w - dw_ref).astype(np.float64)) / np.linalg.norm(dw_ref.astype(np.float64)) <= 1e-5, path
+                eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
+                assert np.array_equal(dw.to_host().view(np.uint32), got_w.view(np.uint32)), path               # deterministic
+            else:                                            # no tensor-core weight gradient for this shape: refused, not rerouted
+                with pytest.raises(pkg.PcnnError, match="pcnn_conv_bwd_select"):
+                    eng.conv_wgrad(dxb, dyb, dw, N, H, W, C, K, R, S)
+            dxo = eng.array((N, H, W, C), np.uint16)
+            eng.conv_dgrad(dyb, fd, dxo, N, H, W, C, K, R, S)
+            got_x = pkg.bf16_bits_to_f32(dxo.to_host())
+            assert np.all(np.abs(got_x - dx_ref) <= 2.0 ** -8 * np.abs(dx_ref) + 1e-3), path
+            res[path] = (got_w, got_x, eng.launch_count() - launches0)
+    finally:
+        eng.conv_bwd_select(reference=False)
     # the two paths are different kernels (the dgrad launch counts differ: the tensor-core path also builds its filter variants)
     assert res["tc"][2] != res["fma"][2]
-    assert np.linalg.norm(res["tc"][0] - res["fma"][0]) / np.linalg.norm(res["fma"][0]) <= 1e-5
+    if wgrad_tc:
+        assert np.linalg.norm(res["tc"][0] - res["fma"][0]) / np.linalg.norm(res["fma"][0]) <= 1e-5
 
 
 def test_tensor_core_dgrad_honours_row_and_image_pitch(eng, pkg):
