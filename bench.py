@@ -444,6 +444,23 @@ def run_ours(a):
                  "steps": K4, "unit": "images/s",
                  "parity_note": "batches beyond the oracle's reach are covered by additivity / determinism tests (tests/test_fused_gpu.py)"}
 
+    # ---- phase trace of the persistent kernel at this N (CTA 0 of every rank; rank 0's is printed): where a step's time goes
+    phases = None
+    if a.mode != "graph" and not a.no_phase_trace:
+        eng.train_steps(0, B, 50)
+        barrier()
+        eng.persist_trace_arm()
+        eng.train_steps(-1, B, 256)
+        eng.sync()
+        tr = eng.persist_trace_read(256)[8:]
+        dd = np.diff(tr, axis=1).astype(np.float64) / 1e3
+        stepus = np.diff(tr[:, 0]).astype(np.float64) / 1e3
+        names = ["param_fetch", "images", "epilogue+cluster_reduce", "owner_gather", "exchange+update+publish"]
+        phases = {"step_us_median": float(np.median(stepus)), "unit": "us", "view": "CTA 0 of rank 0, %globaltimer (0.26 us resolution)"}
+        phases.update({n: float(np.median(dd[:, i])) for i, n in enumerate(names)})
+        phases.update(eng.persist_info())
+        barrier()
+
     # ---- roofline of the dominant kernel + live fp32 peak
     line = None
     if rank == 0:
@@ -510,7 +527,7 @@ def run_ours(a):
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * 785 * world,
                     "d2h_bytes_per_step": 4 * world, "steps": K2, "api": "Engine.learn_host (pcnn_learn_host), pinned host u8"},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "ref_gpu_baseline": ref_gpu, "clocks": clocks,
-            "parity": parity, "batch1024": b1024, "conv": conv,
+            "parity": parity, "batch1024": b1024, "phase_trace": phases, "conv": conv,
         }
         print(json.dumps(line), flush=True)
     eng.close()
@@ -529,6 +546,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-conv", action="store_true", help="skip the conv fwd+bwd roofline block (N = 1 only)")
     ap.add_argument("--persist-tune", type=int, default=0, help="pcnn_persist_tune knob (profiling runs: 2 = clusters without the cooperative attribute)")
+    ap.add_argument("--no-phase-trace", action="store_true", help="skip the per-phase trace of the persistent kernel")
     ap.add_argument("--no-batch1024", action="store_true", help="skip the 1024-per-GPU / global-8192 block")
     ap.add_argument("--mode", default="auto", choices=["auto", "graph", "persistent"],
                     help="auto/persistent: one cooperative kernel runs all K steps (N > 1: in-kernel NVLink exchange); "

@@ -18,7 +18,7 @@ for MODE in ${MODES:-persistent graph}; do
 import json
 try:
     d=json.loads(open("$OUT/bench_n${N}_$MODE.json").read().strip().splitlines()[-1])
-    print({k:d[k] for k in ("value","n_gpus","ms_per_step")}, "e2e", d["e2e"]["value"], d["config"]["step_mode"], "parity", d.get("parity"), "b1024", d.get("batch1024"))
+    print({k:d[k] for k in ("value","n_gpus","ms_per_step")}, "e2e", d["e2e"]["value"], d["config"]["step_mode"], "parity", d.get("parity"), "b1024", d.get("batch1024"), "phases", d.get("phase_trace"))
 except Exception as e:
     print("no json", e); print(open("$OUT/bench_n${N}_$MODE.err").read()[-1500:])
 PY
