@@ -333,11 +333,23 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def aligned_start():
+        """All ranks leave at the same instant of the node's monotonic clock (single node: one clock): a collective barrier
+        alone releases the ranks tens of microseconds apart, which a short timed region would count as step time."""
+        if world == 1:
+            return
+        tgt = torch.tensor([time.monotonic() + 0.003], dtype=torch.float64, device="cuda")
+        dist.broadcast(tgt, src=0)
+        t_go = float(tgt.item())
+        while time.monotonic() < t_go:
+            pass
+
     def timed_steps(batch, k, w):
         """w warm-up + k timed cursor-driven steps of `batch` images per GPU; returns ms (max over ranks)."""
         eng.train_steps_prepare(batch, k)
         eng.train_steps(0, batch, w)
         barrier()
+        aligned_start()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record(stream)
         eng.train_steps(-1, batch, k)
@@ -395,6 +407,7 @@ def run_ours(a):
     eng.train_steps_prepare(B, K)            # instantiate the step graphs the timed call replays (host work, untimed)
     eng.train_steps(0, B, W)                 # W untimed warm-up steps
     barrier()
+    aligned_start()
     l0 = eng.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
@@ -420,6 +433,7 @@ def run_ours(a):
     hl.numpy()[:] = labs[sel]
     eng.learn_host(hi.numpy(), hl.numpy(), B=B, epochs=1)            # warm-up pass (graphs, staging buffers)
     barrier()
+    aligned_start()
     t0 = time.perf_counter()
     eng.learn_host(hi.numpy(), hl.numpy(), B=B, epochs=1)            # returns when the last step's result is on the host
     torch.cuda.synchronize()
