@@ -207,9 +207,10 @@ int pcnn_p2p_detach(pcnn_ctx *ctx);
 int pcnn_set_step_mode(pcnn_ctx *ctx, int mode);
 /* Geometry of the most recent persistent launch and what the device can hold: out6 = { grid, cluster size, co-resident CTAs,
  * co-resident CTAs when launched as clusters, the cluster size the kernel is built for, 1 if the launches are cooperative }.
- * pcnn_persist_tune(ctx, 1) forces the variant without clusters (0 = automatic), 2 keeps the clusters but launches without
- * the cooperative attribute (profilers that re-issue cooperative launches drop the cluster dimension) -- measurement knobs
- * for the runs under profiles/. */
+ * pcnn_persist_tune(ctx, mask): bit 0 forces the variant without clusters; bit 1 keeps the clusters but launches without the
+ * cooperative attribute (profilers that re-issue cooperative launches drop the cluster dimension); bit 2 makes
+ * pcnn_learn_host enqueue its host copies BEFORE the kernel launch (needed wherever launches block the calling thread:
+ * kernel-replay profilers; CUDA_LAUNCH_BLOCKING=1 is detected by itself).  Measurement knobs for the runs under profiles/. */
 int pcnn_persist_info(pcnn_ctx *ctx, int *out6);
 int pcnn_persist_tune(pcnn_ctx *ctx, int max_cluster);
 /* Phase timestamps of the persistent kernel (ns; 6 per step: step start, parameters resident, images done, cluster slot
@@ -227,6 +228,22 @@ int pcnn_maxpool_bwd(pcnn_ctx *ctx, const float *dout, const int32_t *argmax, fl
 /* softmax cross-entropy over n logits per row; d = onehot - p (the reference's sign convention for d_preact) */
 int pcnn_softmax_ce(pcnn_ctx *ctx, const float *logits, const uint8_t *labels, int B, int n, float *prob,
                     float *d, float *loss);
+
+/* ------------------------------------------------------------------ LeNet-5-style variant with a second convolution layer
+ * (PARITY UNPINNED: the reference has exactly one conv layer, layer.h:105-140 / Main.cpp:17-20).
+ *     28x28 -> c1 6@5x5 -> s2 shared 2x2/2 weighted sum -> c3 16@5x5 over 6 channels -> s4 shared 2x2/2 -> f 256 -> 10,
+ * sigmoid everywhere, the reference's loss (d_preact_f = onehot - output) and its gradient / update rules generalised by
+ * rule; oracle/lenet5_oracle.c is the definition.  Packed parameters, PCNN_L5_NPARAM = 5,152 floats:
+ *     c1w 150 | c1b 6 | s2w 4 | s2b 1 | c3w [16][6][5][5] 2400 | c3b 16 | s4w 4 | s4b 1 | fw [10][256] 2560 | fb 10.
+ * All pointers are device pointers; grads_dev holds PCNN_L5_NPARAM + 1 floats (packed gradient, then the batch sum of
+ * error norms) and may be NULL for pcnn_l5_train_step.  One fused kernel per batch (activations and parameters in shared
+ * memory) + a fixed-order slot reduction: deterministic.  Update: w += (dt / B) * g with the bias divisors of the rules. */
+#define PCNN_L5_NPARAM 5152
+int pcnn_l5_compute_grads(pcnn_ctx *ctx, const float *params_dev, const void *images_dev, int pixel_type,
+                          const uint8_t *labels_dev, int B, float *grads_dev);
+int pcnn_l5_train_step(pcnn_ctx *ctx, float *params_dev, const void *images_dev, int pixel_type, const uint8_t *labels_dev,
+                       int B, float *grads_dev);
+int pcnn_l5_forward(pcnn_ctx *ctx, const float *params_dev, const void *images_dev, int pixel_type, int B, float *f_out_dev);
 
 /* ------------------------------------------------------------------ bf16 tensor-core convolution (BASELINE configs 3, 5)
  * The reference's conv semantics (valid, stride 1, cross-correlation, layer.h:118-130) generalised to C input channels,

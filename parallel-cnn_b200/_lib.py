@@ -103,6 +103,9 @@ _SIG = {
     "pcnn_persist_trace_ctas": [_vp, _vp, _i],
     "pcnn_persist_info": [_vp, _vp],
     "pcnn_conv_bwd_select": [_vp, _i],
+    "pcnn_l5_compute_grads": [_vp, _vp, _vp, _i, _vp, _i, _vp],
+    "pcnn_l5_train_step": [_vp, _vp, _vp, _i, _vp, _i, _vp],
+    "pcnn_l5_forward": [_vp, _vp, _vp, _i, _i, _vp],
     "pcnn_persist_tune": [_vp, _i],
     "pcnn_maxpool_fwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
     "pcnn_maxpool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],

@@ -659,8 +659,12 @@ static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel
                 gate.chunk_samples = chunk;
                 *ctx->h_hs_tag = gate.tag;   // the previous user of this word has been synchronised with (end of every launch)
                 // The kernel goes first: it sets itself up while the host enqueues the copies, and waits on the flag of a
-                // sample's chunk before it touches the sample.
-                if ((rc = pcnn_persist_run(ctx, tmp, B, steps, &gate, ctx->h_step_err + steps_done, fresh, last ? ctx->h_hs_done : nullptr,
+                // sample's chunk before it touches the sample.  Where kernel launches block the calling thread until the
+                // kernel has finished (CUDA_LAUNCH_BLOCKING=1, profilers that replay kernels) the copies must be enqueued
+                // before the launch instead, or the kernel would wait for chunks nobody can enqueue.
+                const bool copies_first = ctx->hs_copies_first;
+                if (!copies_first &&
+                    (rc = pcnn_persist_run(ctx, tmp, B, steps, &gate, ctx->h_step_err + steps_done, fresh, last ? ctx->h_hs_done : nullptr,
                                            done_tag)))
                     return rc;
                 PCNN_CUDA(cudaMemcpyAsync(ctx->d_hs_labels, host_labels + off, (size_t)sn, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -673,6 +677,10 @@ static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel
                     PCNN_CUDA(cudaMemcpyAsync(ctx->d_hs_ready + k, ctx->h_hs_tag, sizeof(unsigned), cudaMemcpyHostToDevice, ctx->copy_stream));
                     co += cs;
                 }
+                if (copies_first &&
+                    (rc = pcnn_persist_run(ctx, tmp, B, steps, &gate, ctx->h_step_err + steps_done, fresh, last ? ctx->h_hs_done : nullptr,
+                                           done_tag)))
+                    return rc;
             }
             steps_done += steps;
             if (last) {

@@ -86,6 +86,10 @@ extern "C" int pcnn_create(pcnn_ctx **out, int device, void *stream) {
         if (rc) return rc;
         if ((rc = pcnn_persist_configure(c))) return rc;
     }
+    {   // a CUDA runtime setting, not a knob of this library: blocking launches change the order pcnn_learn_host must enqueue in
+        const char *lb = getenv("CUDA_LAUNCH_BLOCKING");
+        c->hs_copies_first = lb && lb[0] == '1';
+    }
     // default parameters = the reference's static-constructor state
     float init[NPARAM];
     pcnn_init_params_reference(init);

@@ -96,6 +96,7 @@ struct pcnn_ctx {
     size_t hs_image_bytes = 0;
     long hs_label_cap = 0, hs_ready_cap = 0;
     unsigned hs_serial = 0;
+    bool hs_copies_first = false;           // launches block the host thread (CUDA_LAUNCH_BLOCKING, kernel-replay profilers)
     double *h_hs_done = nullptr;            // pinned {double error sum, unsigned tag} written by the kernel after its last step
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};

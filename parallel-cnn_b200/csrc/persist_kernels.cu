@@ -781,10 +781,11 @@ extern "C" int pcnn_persist_info(pcnn_ctx *ctx, int *out6) {
 
 extern "C" int pcnn_persist_tune(pcnn_ctx *ctx, int max_cluster) {
     PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_persist_tune: ctx is NULL");
-    PCNN_REQUIRE(max_cluster >= 0 && max_cluster <= 2, PCNN_ERR_ARG,
-                 "pcnn_persist_tune: 0 (automatic), 1 (no clusters) or 2 (clusters without the cooperative attribute)");
-    ctx->persist_force_cluster = max_cluster == 1 ? 1 : 0;
-    if (max_cluster == 2) ctx->persist_no_coop = true;
+    PCNN_REQUIRE(max_cluster >= 0 && max_cluster <= 7, PCNN_ERR_ARG,
+                 "pcnn_persist_tune: bit mask of 1 (no clusters), 2 (clusters without the cooperative attribute), 4 (host copies before the launch)");
+    ctx->persist_force_cluster = (max_cluster & 1) ? 1 : 0;
+    if (max_cluster & 2) ctx->persist_no_coop = true;
+    if (max_cluster & 4) ctx->hs_copies_first = true;
     return PCNN_OK;
 }
 

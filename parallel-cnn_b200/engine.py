@@ -356,6 +356,16 @@ class Engine:
     def maxpool_bwd(self, dout, argmax, din, planes, H, W, k):
         self._call("pcnn_maxpool_bwd", _p(dout), _p(argmax), _p(din), int(planes), int(H), int(W), int(k))
 
+    # LeNet-5-style variant (second convolution layer); all arguments are DeviceArrays
+    def l5_compute_grads(self, params, images, pixel_type, labels, B, grads):
+        self._call("pcnn_l5_compute_grads", _p(params), _p(images), int(pixel_type), _p(labels), int(B), _p(grads))
+
+    def l5_train_step(self, params, images, pixel_type, labels, B, grads=None):
+        self._call("pcnn_l5_train_step", _p(params), _p(images), int(pixel_type), _p(labels), int(B), _p(grads) if grads is not None else None)
+
+    def l5_forward(self, params, images, pixel_type, B, f_out):
+        self._call("pcnn_l5_forward", _p(params), _p(images), int(pixel_type), int(B), _p(f_out))
+
     def conv_bwd_select(self, reference=False):
         """reference=True: the FMA-pipe reference kernels for every shape (explicit opt-in); False: tensor cores only"""
         self._call("pcnn_conv_bwd_select", 1 if reference else 0)

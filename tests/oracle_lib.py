@@ -121,6 +121,57 @@ def reference(native=False):
     return _ref
 
 
+# ---------------------------------------------------------------- LeNet-5-style variant (oracle/lenet5_oracle.c; parity unpinned)
+L5_SO = os.path.join(ROOT, "oracle", "liblenet5_oracle.so")
+L5_NPARAM = 5152
+L5_OFF = dict(c1w=(0, 150), c1b=(150, 156), s2w=(156, 160), s2b=(160, 161), c3w=(161, 2561), c3b=(2561, 2577), s4w=(2577, 2581),
+              s4b=(2581, 2582), fw=(2582, 5142), fb=(5142, 5152))
+_l5 = None
+
+
+def lenet5():
+    global _l5
+    if _l5 is None:
+        if not os.path.exists(L5_SO):
+            raise RuntimeError(f"{L5_SO} missing: run `make -C oracle` (or __graft_entry__.build())")
+        L = C.CDLL(L5_SO)
+        assert L.l5_nparam() == L5_NPARAM
+        L.l5_init_params.argtypes = [_f, C.c_uint32]
+        L.l5_batch_grad.argtypes = [_f, _f, _u8, C.c_long, _d, _d]
+        L.l5_apply_update.argtypes = [_f, _f, C.c_float]
+        L.l5_forward_out.argtypes = [_f, _f, _f]
+        _l5 = L
+    return _l5
+
+
+def l5_init_params(seed=1):
+    p = np.empty(L5_NPARAM, np.float32)
+    lenet5().l5_init_params(fp(p), seed)
+    return p
+
+
+def l5_batch_grad(p, imgs_f32, labels):
+    """sum over the batch of the packed (negative) gradient (float64) and the sum of error norms"""
+    imgs = np.ascontiguousarray(imgs_f32, np.float32).reshape(-1, 784)
+    labs = np.ascontiguousarray(labels, np.uint8)
+    g = np.zeros(L5_NPARAM, np.float64)
+    e = np.zeros(1, np.float64)
+    lenet5().l5_batch_grad(fp(np.ascontiguousarray(p, np.float32)), fp(imgs.reshape(-1)), u8p(labs), imgs.shape[0], dp(g), dp(e))
+    return g, float(e[0])
+
+
+def l5_apply_update(p, g_f32, step):
+    q = np.array(p, np.float32, copy=True)
+    lenet5().l5_apply_update(fp(q), fp(np.ascontiguousarray(g_f32, np.float32)), np.float32(step))
+    return q
+
+
+def l5_forward_out(p, img_f32):
+    out = np.empty(10, np.float32)
+    lenet5().l5_forward_out(fp(np.ascontiguousarray(p, np.float32)), fp(np.ascontiguousarray(img_f32, np.float32).reshape(-1)), fp(out))
+    return out
+
+
 # ---------------------------------------------------------------- convenience wrappers over the oracle
 def init_params():
     p = np.empty(NPARAM, np.float32)

@@ -179,3 +179,36 @@ def test_reference_static_constructor_state_equals_seed1_redraw(golden):
     ref.ref_get_params(O.fp(p))
     assert np.array_equal(bits(p), bits(golden["params_init"]))
     assert ref.ref_sizeof_mnist_data() == 6280            # Appendix B
+
+
+def test_lenet5_variant_oracle_backward_is_the_gradient_of_its_forward(golden):
+    """oracle/lenet5_oracle.c is self-written (the reference has no second conv layer): its backward pass is pinned to its
+    own forward pass by a finite-difference check.  With d_preact_f = onehot - output (layer.h:91-95) the packed vector is
+    the negative gradient of the summed binary cross-entropy of the ten sigmoid outputs, up to the normalisation rules
+    (conv weight blocks divided by the map size: 576 for c1, 64 for c3)."""
+    p0 = O.l5_init_params(7).astype(np.float64)
+    img = O.u8_to_f32(golden["train_u8"][3])
+    y = int(golden["train_labels"][3])
+    t = np.zeros(10)
+    t[y] = 1.0
+
+    def loss(pv):
+        o = O.l5_forward_out(pv.astype(np.float32), img).astype(np.float64)
+        return -np.sum(t * np.log(o) + (1 - t) * np.log(1 - o))
+
+    g, err = O.l5_batch_grad(p0.astype(np.float32), img[None], np.array([y], np.uint8))
+    assert np.isfinite(g).all() and err > 0
+    scale = np.ones(O.L5_NPARAM)
+    scale[slice(*O.L5_OFF["c1w"])] = 576.0
+    scale[slice(*O.L5_OFF["c3w"])] = 64.0
+    rng = np.random.default_rng(0)
+    picks = np.concatenate([rng.choice(np.arange(*O.L5_OFF[k]), size=min(6, O.L5_OFF[k][1] - O.L5_OFF[k][0]), replace=False)
+                            for k in O.L5_OFF])
+    for j in picks:
+        eps = 2e-2
+        pp, pm = p0.copy(), p0.copy()
+        pp[j] += eps
+        pm[j] -= eps
+        num = -(loss(pp) - loss(pm)) / (2 * eps)            # negative gradient, like the packed vector
+        ana = g[j] * scale[j]
+        assert abs(num - ana) <= 3e-2 * max(abs(ana), abs(num)) + 2e-4, (int(j), num, ana)
