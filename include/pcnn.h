@@ -258,6 +258,12 @@ int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int C, int K, i
                              int image_rows /* rows between consecutive images in memory, >= H; 0 = H.  A multiple of
                                                32 lets the epilogue use asynchronous TMA stores */,
                              int act, const float *filt_host, const float *bias_host, pcnn_conv_plan **plan_out);
+/* the same with a window step of `stride` (1..4) in both directions: y [N][(H-R)/stride+1][(W-S)/stride+1][K];
+ * rows per image (image_rows, or H) must be a multiple of the stride; the pixel block then needs ((Qt-1)*stride+S)*C <= 32.
+ * Backward passes of strided convolutions are not built. */
+int pcnn_conv_tc_plan_create_strided(pcnn_ctx *ctx, int N, int H, int W, int C, int K, int R, int S, int stride, int row_pitch,
+                                     int image_rows, int act, const float *filt_host, const float *bias_host,
+                                     pcnn_conv_plan **plan_out);
 int pcnn_conv_tc_plan_destroy(pcnn_ctx *ctx, pcnn_conv_plan *plan);
 int pcnn_conv_tc_fwd(pcnn_ctx *ctx, pcnn_conv_plan *plan, const void *x_bf16_dev, void *y_bf16_dev);
 /* Backward passes of the same convolution (bf16 operands, fp32 accumulation, deterministic; tcgen05 kernels, see

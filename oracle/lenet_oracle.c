@@ -429,6 +429,24 @@ void orc_conv_fwd_nhwc(const float *x, const float *w, const float *bias, float 
                     y[(((long)n * P + p) * Q + q) * K + k] = (float)acc;
                 }
 }
+/* the same with a window step of `stride` in both directions (the reference's conv is stride 1):
+ * y [N][(H-R)/stride+1][(W-S)/stride+1][K] */
+void orc_conv_fwd_nhwc_strided(const float *x, const float *w, const float *bias, float *y,
+                               int N, int H, int W, int C, int K, int R, int S, int stride) {
+    int P = (H - R) / stride + 1, Q = (W - S) / stride + 1;
+    for (int n = 0; n < N; ++n)
+        for (int p = 0; p < P; ++p)
+            for (int q = 0; q < Q; ++q)
+                for (int k = 0; k < K; ++k) {
+                    double acc = bias ? (double)bias[k] : 0.0;
+                    for (int r = 0; r < R; ++r)
+                        for (int s = 0; s < S; ++s)
+                            for (int c = 0; c < C; ++c)
+                                acc += (double)x[(((long)n * H + p * stride + r) * W + q * stride + s) * C + c] *
+                                       (double)w[((k * R + r) * S + s) * C + c];
+                    y[(((long)n * P + p) * Q + q) * K + k] = (float)acc;
+                }
+}
 /* x3 wgrad: dw[k][r][s][c] = sum_{n,p,q} dy[n][p][q][k] * x[n][p+r][q+s][c]   (layer.h:371-395 without /576) */
 void orc_conv_wgrad_nhwc(const float *x, const float *dy, float *dw,
                          int N, int H, int W, int C, int K, int R, int S) {

@@ -111,6 +111,7 @@ _SIG = {
     "pcnn_maxpool_bwd": [_vp, _vp, _vp, _vp, _i, _i, _i, _i],
     "pcnn_softmax_ce": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
     "pcnn_conv_tc_plan_create": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _pvp],
+    "pcnn_conv_tc_plan_create_strided": [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _pvp],
     "pcnn_conv_tc_plan_destroy": [_vp, _vp],
     "pcnn_conv_tc_fwd": [_vp, _vp, _vp, _vp],
     "pcnn_f32_to_bf16_rows": [_vp, _vp, _vp, _l, _i, _i],

@@ -43,7 +43,10 @@ constexpr int OUT_STAGE_BYTES = 2 * 4096;            // per epilogue warp: two [
 struct ConvTcParams {
     int n_img, H, P, Q, K, R;      // images, input rows per image, valid output rows/cols, filters, filter rows
     int Qt, ncols;                 // output pixels per tile, Qt * K
-    int C;                         // input channels (column offset of a tile = q0 * C elements)
+    int C;                         // input channels (column offset of a tile = q0 * stride * C elements)
+    int stride;                    // step of the window in both directions (1 = the reference's conv, layer.h:118-130)
+    int x_pitch;                   // elements between input rows: filter row r of a stride-s conv reads view row r / s at
+                                   // column offset (r % s) * x_pitch of the input viewed as [N * H / s][s * x_pitch]
     int V;                         // Toeplitz variants: the box start is rounded down to 8 elements (16 B, a TMA
                                    // requirement on the global address), the remainder (q0*C) % 8 selects the variant
     int stages;                    // activation stages that fit next to the V * R Toeplitz matrices
@@ -121,7 +124,8 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 const int mt = tile / p.n_qtiles, qt = tile % p.n_qtiles;
                 bar_expect_tx(&S.full[stage], (unsigned)(p.R * A_TILE_BYTES));
                 for (int r = 0; r < p.R; ++r)
-                    tma_load_2d(sv.a(stage, r), &map_x, (qt * p.Qt * p.C) & ~7, mt * TC_M + r, &S.full[stage]);
+                    tma_load_2d(sv.a(stage, r), &map_x, ((qt * p.Qt * p.stride * p.C) & ~7) + (r % p.stride) * p.x_pitch,
+                                mt * TC_M + r / p.stride, &S.full[stage]);
             }
         }
     } else if (warp == 1) {
@@ -317,7 +321,7 @@ int make_map_y(CUtensorMap *map, void *base, uint64_t row_elems, uint64_t P, uin
 
 struct pcnn_conv_plan {
     ConvTcParams p;
-    int W, S, row_pitch;
+    int W, S, row_pitch, stride, in_image_rows;
     void *d_toeplitz = nullptr;     // [R][ncols][32] bf16
     float *d_bias = nullptr;
     CUtensorMap map_b;
@@ -333,14 +337,24 @@ static void free_plan(pcnn_conv_plan *plan) {
 extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int C, int K, int R, int S, int row_pitch,
                                         int image_rows, int act, const float *filt_host, const float *bias_host,
                                         pcnn_conv_plan **out) {
+    return pcnn_conv_tc_plan_create_strided(ctx, N, H, W, C, K, R, S, 1, row_pitch, image_rows, act, filt_host, bias_host, out);
+}
+
+extern "C" int pcnn_conv_tc_plan_create_strided(pcnn_ctx *ctx, int N, int H, int W, int C, int K, int R, int S, int stride, int row_pitch,
+                                                int image_rows, int act, const float *filt_host, const float *bias_host,
+                                                pcnn_conv_plan **out) {
     PCNN_REQUIRE(ctx && filt_host && out, PCNN_ERR_ARG, "pcnn_conv_tc_plan_create: NULL argument");
+    PCNN_REQUIRE(stride >= 1 && stride <= 4, PCNN_ERR_ARG, "pcnn_conv_tc_plan_create: stride %d outside 1..4", stride);
     PCNN_REQUIRE(N > 0 && H >= R && W >= S && C > 0 && K > 0 && R > 0 && R <= TC_MAX_R && S > 0, PCNN_ERR_ARG,
                  "pcnn_conv_tc_plan_create: bad shape N=%d H=%d W=%d C=%d K=%d R=%d S=%d", N, H, W, C, K, R, S);
     PCNN_REQUIRE(row_pitch >= W * C && row_pitch % 8 == 0, PCNN_ERR_ARG,
                  "pcnn_conv_tc_plan_create: row pitch %d must be >= W*C and a multiple of 8 elements (TMA 16-byte strides)", row_pitch);
     if (image_rows <= 0) image_rows = H;
     PCNN_REQUIRE(image_rows >= H, PCNN_ERR_ARG, "pcnn_conv_tc_plan_create: image pitch of %d rows is smaller than H = %d", image_rows, H);
-    const int Q = W - S + 1, P = H - R + 1;
+    PCNN_REQUIRE(image_rows % stride == 0, PCNN_ERR_ARG,
+                 "pcnn_conv_tc_plan_create: rows per image (%d) must be a multiple of the stride %d (the input is addressed as [N * rows / stride] "
+                 "rows of stride * pitch elements)", image_rows, stride);
+    const int Q = (W - S) / stride + 1, P = (H - R) / stride + 1;
     // pixel block Qt: the TMA box must start on a 16-byte boundary, so it starts at (q0*C) & ~7 and the Toeplitz
     // operand absorbs the remainder delta = (q0*C) % 8: delta + (Qt+S-1)*C elements must fit the 32-element K chunk.
     // q0 = qt * Qt, so delta cycles with period V = 8 / gcd(8, Qt*C); each remainder needs its own operand copy.
@@ -349,41 +363,43 @@ extern "C" int pcnn_conv_tc_plan_create(pcnn_ctx *ctx, int N, int H, int W, int 
     for (int t = Q; t >= 1 && !Qt; --t) {
         if (t * K > 256 || (t * K) % 16 != 0) continue;
         const int single = ((Q + t - 1) / t) == 1;                       // one block per row: delta is always 0
-        const int v = single ? 1 : 8 / gcd(8, (t * C) % 8 == 0 ? 8 : (t * C) % 8);
+        const int v = single ? 1 : 8 / gcd(8, (t * stride * C) % 8 == 0 ? 8 : (t * stride * C) % 8);
         int max_delta = 0;
-        for (int i = 0; i < v; ++i) max_delta = max_delta > (i * t * C) % 8 ? max_delta : (i * t * C) % 8;
-        if (max_delta + (t + S - 1) * C > TC_KCHUNK) continue;
+        for (int i = 0; i < v; ++i) max_delta = max_delta > (i * t * stride * C) % 8 ? max_delta : (i * t * stride * C) % 8;
+        if (max_delta + ((t - 1) * stride + S) * C > TC_KCHUNK) continue;
         const size_t fixed = (size_t)v * R * t * K * TC_KCHUNK * 2 + TC_EPI_WARPS * OUT_STAGE_BYTES + sizeof(ConvTcCtl) + 1024;
         if (fixed + 2 * (size_t)R * A_TILE_BYTES > (size_t)TC_SMEM_BUDGET) continue;
         int st = (int)(((size_t)TC_SMEM_BUDGET - fixed) / ((size_t)R * A_TILE_BYTES));
         Qt = t; V = v; stages = st > TC_MAX_STAGES ? TC_MAX_STAGES : st;
     }
     PCNN_REQUIRE(Qt > 0, PCNN_ERR_ARG,
-                 "pcnn_conv_tc_plan_create: no pixel block with (Qt+S-1)*C (+ alignment remainder) <= 32, Qt*K <= 256, %%16 == 0");
+                 "pcnn_conv_tc_plan_create: no pixel block with ((Qt-1)*stride+S)*C (+ alignment remainder) <= 32, Qt*K <= 256, %%16 == 0");
     pcnn_device_guard g(ctx->device);
     struct PlanGuard {                       // frees a half-built plan on every early return below
         pcnn_conv_plan *p;
         ~PlanGuard() { free_plan(p); }
     } guard{new pcnn_conv_plan()};
     pcnn_conv_plan *pl = guard.p;
-    pl->W = W; pl->S = S; pl->row_pitch = row_pitch;
+    pl->W = W; pl->S = S; pl->row_pitch = row_pitch; pl->stride = stride; pl->in_image_rows = image_rows;
     ConvTcParams &p = pl->p;
-    p.n_img = N; p.H = image_rows; p.P = P; p.Q = Q; p.K = K; p.R = R; p.Qt = Qt; p.ncols = Qt * K; p.C = C; p.V = V; p.stages = stages;
-    p.n_mtiles = (int)(((long long)N * image_rows + TC_M - 1) / TC_M);
+    // rows are counted in units of `stride` input rows: tile row m = n * (image_rows / stride) + p
+    p.n_img = N; p.H = image_rows / stride; p.P = P; p.Q = Q; p.K = K; p.R = R; p.Qt = Qt; p.ncols = Qt * K; p.C = C; p.V = V; p.stages = stages;
+    p.stride = stride; p.x_pitch = row_pitch;
+    p.n_mtiles = (int)(((long long)N * p.H + TC_M - 1) / TC_M);
     p.n_qtiles = (Q + Qt - 1) / Qt;
     p.act = act;
     p.y_row_elems = (long long)Q * K;
-    p.tma_store = (image_rows % 32 == 0 && ((long long)Q * K * 2) % 16 == 0) ? 1 : 0;
+    p.tma_store = (p.H % 32 == 0 && ((long long)Q * K * 2) % 16 == 0) ? 1 : 0;
     // Toeplitz operands: T_{v,r}[(ql, k)][kk] = f[k][r][s][c] where kk = delta_v + (ql + s) * C + c
     std::vector<uint16_t> t((size_t)V * R * p.ncols * TC_KCHUNK, 0);
     for (int v = 0; v < V; ++v) {
-        const int delta = (v * Qt * C) % 8;
+        const int delta = (v * Qt * stride * C) % 8;
         for (int r = 0; r < R; ++r)
             for (int ql = 0; ql < Qt; ++ql)
                 for (int k = 0; k < K; ++k)
                     for (int s = 0; s < S; ++s)
                         for (int c = 0; c < C; ++c)
-                            t[(((size_t)v * R + r) * p.ncols + ql * K + k) * TC_KCHUNK + delta + (ql + s) * C + c] =
+                            t[(((size_t)v * R + r) * p.ncols + ql * K + k) * TC_KCHUNK + delta + (ql * stride + s) * C + c] =
                                 f32_to_bf16_bits(filt_host[(((size_t)k * R + r) * S + s) * C + c]);
     }
     PCNN_CUDA(cudaMalloc(&pl->d_toeplitz, t.size() * 2));
@@ -421,8 +437,9 @@ extern "C" int pcnn_conv_tc_fwd(pcnn_ctx *ctx, pcnn_conv_plan *plan, const void 
     ConvTcParams p = plan->p;
     p.y = reinterpret_cast<__nv_bfloat16 *>(y_bf16);
     CUtensorMap map_x;
-    int rc = make_map_2d(&map_x, const_cast<void *>(x_bf16), (uint64_t)plan->row_pitch, (uint64_t)p.n_img * p.H,
-                         (uint64_t)plan->row_pitch * 2, TC_KCHUNK, TC_M);
+    // stride s: the input viewed as [N * rows / s] rows of s * pitch elements (see ConvTcParams::x_pitch)
+    int rc = make_map_2d(&map_x, const_cast<void *>(x_bf16), (uint64_t)plan->row_pitch * plan->stride, (uint64_t)p.n_img * p.H,
+                         (uint64_t)plan->row_pitch * plan->stride * 2, TC_KCHUNK, TC_M);
     if (rc) return rc;
     CUtensorMap map_y = map_x;                          // placeholder when the direct-store epilogue is used
     if (p.tma_store) {

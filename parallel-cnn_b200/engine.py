@@ -389,7 +389,7 @@ class Engine:
 class ConvPlan:
     """bf16 tensor-core convolution plan (pcnn_conv_tc_*): filters fp32 KRSC on the host, activations NHWC bf16."""
 
-    def __init__(self, engine, N, H, W, C, K, R, S, filt, bias=None, act=0, row_pitch=None, image_rows=0):
+    def __init__(self, engine, N, H, W, C, K, R, S, filt, bias=None, act=0, row_pitch=None, image_rows=0, stride=1):
         self.engine = engine
         self.shape = (N, H, W, C, K, R, S)
         self.row_pitch = int(row_pitch if row_pitch is not None else (W * C + 7) // 8 * 8)
@@ -397,11 +397,11 @@ class ConvPlan:
         assert filt.size == K * R * S * C
         b = None if bias is None else np.ascontiguousarray(bias, np.float32)
         plan = C_.c_void_p()
-        check("pcnn_conv_tc_plan_create",
-              lib().pcnn_conv_tc_plan_create(engine.ctx, N, H, W, C, K, R, S, self.row_pitch, int(image_rows), int(act), filt.ctypes.data,
-                                             None if b is None else b.ctypes.data, C_.byref(plan)))
+        check("pcnn_conv_tc_plan_create_strided",
+              lib().pcnn_conv_tc_plan_create_strided(engine.ctx, N, H, W, C, K, R, S, int(stride), self.row_pitch, int(image_rows), int(act),
+                                                     filt.ctypes.data, None if b is None else b.ctypes.data, C_.byref(plan)))
         self.plan = plan
-        self.out_shape = (N, H - R + 1, W - S + 1, K)
+        self.out_shape = (N, (H - R) // stride + 1, (W - S) // stride + 1, K)
 
     def fwd(self, x_bf16_dev, y_bf16_dev):
         check("pcnn_conv_tc_fwd", lib().pcnn_conv_tc_fwd(self.engine.ctx, self.plan, _p(x_bf16_dev), _p(y_bf16_dev)))

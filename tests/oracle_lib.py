@@ -83,6 +83,7 @@ def oracle():
         L.orc_maxpool_fwd.argtypes = [_f, _f, _i32, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_maxpool_bwd.argtypes = [_f, _i32, _f, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_conv_fwd_nhwc.argtypes = [_f, _f, _f, _f] + [C.c_int] * 7
+        L.orc_conv_fwd_nhwc_strided.argtypes = [_f, _f, _f, _f] + [C.c_int] * 8
         L.orc_conv_wgrad_nhwc.argtypes = [_f, _f, _f] + [C.c_int] * 7
         L.orc_conv_dgrad_nhwc.argtypes = [_f, _f, _f] + [C.c_int] * 7
         assert L.orc_sizeof_acts() == N_ACTS * 4

@@ -14,22 +14,26 @@ import oracle_lib as O
 pytestmark = pytest.mark.gpu
 
 
-def conv_case(eng, pkg, N, H, W, C, K, R, S, act, seed, real=None):
+def conv_case(eng, pkg, N, H, W, C, K, R, S, act, seed, real=None, stride=1):
     rng = np.random.default_rng(seed)
     x = rng.uniform(0, 1, (N, H, W, C)).astype(np.float32) if real is None else real        # config 5: x ~ U[0,1)
     f = rng.uniform(-0.5, 0.5, (K, R, S, C)).astype(np.float32)                                # same law as layer.h:49-52
     b = rng.uniform(-0.5, 0.5, K).astype(np.float32)
     xb = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(x))
     fb = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(f))
-    P, Q = H - R + 1, W - S + 1
+    P, Q = (H - R) // stride + 1, (W - S) // stride + 1
     ref = np.empty((N, P, Q, K), np.float32)
-    O.oracle().orc_conv_fwd_nhwc(O.fp(xb.reshape(-1)), O.fp(fb.reshape(-1)), O.fp(b), O.fp(ref.reshape(-1)), N, H, W, C, K, R, S)
+    O.oracle().orc_conv_fwd_nhwc_strided(O.fp(xb.reshape(-1)), O.fp(fb.reshape(-1)), O.fp(b), O.fp(ref.reshape(-1)), N, H, W, C, K, R, S, stride)
+    if stride == 1:          # the strided restatement at stride 1 IS the stride-1 oracle
+        ref1 = np.empty_like(ref)
+        O.oracle().orc_conv_fwd_nhwc(O.fp(xb.reshape(-1)), O.fp(fb.reshape(-1)), O.fp(b), O.fp(ref1.reshape(-1)), N, H, W, C, K, R, S)
+        assert np.array_equal(ref, ref1)
     if act:
         ref = (1.0 / (1.0 + np.exp(-ref.astype(np.float64)))).astype(np.float32)
     pitch = (W * C + 7) // 8 * 8
     xp = np.zeros((N * H, pitch), np.uint16)
     xp[:, : W * C] = pkg.f32_to_bf16_bits(x).reshape(N * H, W * C)
-    plan = pkg.ConvPlan(eng, N, H, W, C, K, R, S, fb, b, act=act, row_pitch=pitch)
+    plan = pkg.ConvPlan(eng, N, H, W, C, K, R, S, fb, b, act=act, row_pitch=pitch, stride=stride)
     dx = eng.to_device(xp)
     dy = eng.array((N, P, Q, K), np.uint16)
     plan.fwd(dx, dy)
@@ -106,6 +110,40 @@ def test_config5_shape(eng, pkg, N, H, W):
 def test_other_small_channel_shapes(eng, pkg):
     conv_case(eng, pkg, 5, 12, 30, 2, 16, 3, 5, act=0, seed=9)      # C = 2, K = 16, 3x5 taps
     conv_case(eng, pkg, 2, 33, 33, 4, 32, 5, 3, act=1, seed=10)     # C = 4, K = 32, 5x3 taps, sigmoid epilogue
+    # the second convolution of the LeNet-5-style variant: 12x12x6 -> 16 filters 5x5, sigmoid epilogue
+    conv_case(eng, pkg, 16, 12, 12, 6, 16, 5, 5, act=1, seed=12)
+
+
+@pytest.mark.parametrize("shape", [(3, 28, 28, 1, 16, 5, 5, 2),      # LeNet-sized input, stride 2: 12 x 12 outputs
+                                   (2, 64, 40, 3, 64, 3, 3, 2),      # config-5-like layer at stride 2 (ragged pixel blocks)
+                                   (1, 224, 224, 3, 64, 3, 3, 2),    # config 5 at stride 2
+                                   (2, 33, 30, 2, 32, 3, 3, 3)])     # stride 3, rows per image padded to a multiple of 3
+def test_strided_convolution(eng, pkg, shape):
+    """window step > 1 in the forward plan (the reference's conv is stride 1, layer.h:118-130), against
+    orc_conv_fwd_nhwc_strided on the bf16-rounded operands."""
+    N, H, W, C, K, R, S, stride = shape
+    if H % stride:                       # rows per image must be a multiple of the stride: pad the image with zero rows
+        Hp = (H + stride - 1) // stride * stride
+        rng = np.random.default_rng(1)
+        x = np.zeros((N, Hp, W, C), np.float32)
+        x[:, :H] = rng.uniform(0, 1, (N, H, W, C)).astype(np.float32)
+        f = rng.uniform(-0.5, 0.5, (K, R, S, C)).astype(np.float32)
+        xb, fb = pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(x)), pkg.bf16_bits_to_f32(pkg.f32_to_bf16_bits(f))
+        P, Q = (H - R) // stride + 1, (W - S) // stride + 1
+        ref = np.empty((N, P, Q, K), np.float32)
+        O.oracle().orc_conv_fwd_nhwc_strided(O.fp(np.ascontiguousarray(xb[:, :H]).reshape(-1)), O.fp(fb.reshape(-1)), O.fp(np.zeros(K, np.float32)),
+                                             O.fp(ref.reshape(-1)), N, H, W, C, K, R, S, stride)
+        pitch = (W * C + 7) // 8 * 8
+        xp = np.zeros((N * Hp, pitch), np.uint16)
+        xp[:, : W * C] = pkg.f32_to_bf16_bits(x).reshape(N * Hp, W * C)
+        plan = pkg.ConvPlan(eng, N, H, W, C, K, R, S, fb, None, act=0, row_pitch=pitch, image_rows=Hp, stride=stride)
+        dy = eng.array((N, P, Q, K), np.uint16)
+        plan.fwd(eng.to_device(xp), dy)
+        got = pkg.bf16_bits_to_f32(dy.to_host())
+        plan.close()
+        assert np.all(np.abs(got - ref) <= 2.0 ** -8 * np.abs(ref) + 1e-3)
+    else:
+        conv_case(eng, pkg, N, H, W, C, K, R, S, act=0, seed=sum(shape), stride=stride)
 
 
 def test_plan_rejects_unsupported_shapes(eng, pkg):
