@@ -472,6 +472,177 @@ __device__ __forceinline__ void cta_epilogue(FusedSmem<InT> &S, const ThreadId &
     if (t == 0) put(OFF_ERR, A.err_acc);
 }
 
+// ----------------------------------------------------------------------------------------------------------------------
+// One image per CTA and step (batch <= grid: the configuration BASELINE.json quotes its metric on): forward + backward + CTA
+// reduction in one piece, specialised on the fact that nothing is accumulated across images:
+//   * the gradient accumulators are not live during the forward pass, so the worker's WHOLE 8x8 input patch stays in
+//     registers from the forward convolution to the weight gradient -- no shared-memory operand inside either FFMA block;
+//   * the f-layer weight gradient (2,160 of the 2,344 packed entries) is pushed to its consumers right after the f layer,
+//     BEFORE the backward convolution, and the s1 sums are reduced there too: what remains for the end of the pass are the
+//     156 c1 entries.
+// `put(p, v)` consumes packed entry p (the persistent kernel pushes it to the cluster rank that owns it).  The image must
+// have been prepared (image_prepare) by the caller; `S.params` must be complete.  Same arithmetic as image_pass + cta_epilogue.
+template <typename InT, typename Sink>
+__device__ __forceinline__ void image_step_single(FusedSmem<InT> &S, const ThreadId &id, int li, bool has_image, const Sink &put) {
+    const int t = id.t, warp = id.warp, lane = id.lane;
+    const int buf = li & 1;
+    __syncthreads();                                                         // sync #1: image + parameters visible
+    const bool work = id.worker && has_image;
+    float o[16];
+    float s1o = 0.0f;
+    float fcp[PCNN_F], fw[PCNN_F];
+#pragma unroll
+    for (int q = 0; q < PCNN_F; ++q) fcp[q] = fw[q] = 0.0f;
+#pragma unroll
+    for (int p = 0; p < 16; ++p) o[p] = 0.0f;
+    const float *ip = S.imgf[buf] + (id.worker ? (4 * id.wx) * 28 + 4 * id.wy : 0);
+    if (work) {
+        float patch[8][8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
+            const float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
+            patch[r][0] = lo.x; patch[r][1] = lo.y; patch[r][2] = lo.z; patch[r][3] = lo.w;
+            patch[r][4] = hi.x; patch[r][5] = hi.y; patch[r][6] = hi.z; patch[r][7] = hi.w;
+        }
+        float acc[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) acc[p] = 0.0f;
+        const float *wc = S.params + OFF_C1W + id.m * 25;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {                                    // fp_c1, layer.h:105-140: terms in (i, j) order
+                const float w = wc[i * 5 + j];
+#pragma unroll
+                for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                    for (int oy = 0; oy < 4; ++oy) acc[ox * 4 + oy] = fmaf(patch[ox + i][oy + j], w, acc[ox * 4 + oy]);
+            }
+        const float bc = S.params[OFF_C1B + id.m];
+        float s1pre = 0.0f;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            o[p] = sigmoid_fast(acc[p] + bc);
+            s1pre = fmaf(S.params[OFF_S1W + p], o[p], s1pre);                // fp_s1, layer.h:143-181
+        }
+        s1o = sigmoid_fast(s1pre + S.params[OFF_S1B]);
+#pragma unroll
+        for (int q = 0; q < PCNN_F; ++q) {                                   // fp_preact_f partial products, layer.h:184-203
+            fw[q] = S.params[OFF_FW + q * PCNN_S1 + t];
+            fcp[q] = fw[q] * s1o;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < PCNN_F; ++q) {
+        const float v = warp_sum(fcp[q]);
+        if (lane == 0) S.fc_red[warp][q] = v;
+    }
+    __syncthreads();                                                         // sync #2
+    // f output, makeError (layer.h:91-95), vectorNorm (Main.cpp:28-34): every warp for itself, d_preact broadcast by shuffle
+    float dq[PCNN_F];
+    float d = 0.0f;
+    if (lane < PCNN_F && has_image) {
+        float pre = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) pre += S.fc_red[w][lane];
+        pre += S.params[OFF_FB + lane];                                      // fp_bias_f, layer.h:206-211
+        d = (lane == S.label[buf] ? 1.0f : 0.0f) - sigmoid_fast(pre);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < PCNN_F; ++q) dq[q] = __shfl_sync(0xffffffffu, d, q);
+    if (warp == 0) {
+        if (lane < PCNN_F) put(OFF_FB + lane, d);                            // bp_bias_f accumulator, layer.h:229-234
+        if (lane == 0) {
+            float ss = 0.0f;
+#pragma unroll
+            for (int q = 0; q < PCNN_F; ++q) ss = fmaf(dq[q], dq[q], ss);
+            put(OFF_ERR, has_image ? sqrtf(ss) : 0.0f);
+        }
+    }
+    __syncwarp();
+    // backward chain (Main.cpp:114-131)
+    float dpc[16], dws[17];
+    float bsum_c1 = 0.0f;
+#pragma unroll
+    for (int p = 0; p < 16; ++p) dpc[p] = 0.0f;
+#pragma unroll
+    for (int p = 0; p < 17; ++p) dws[p] = 0.0f;
+    if (id.worker) {
+        float dout_s1 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < PCNN_F; ++q) {
+            put(OFF_FW + q * PCNN_S1 + t, dq[q] * s1o);                      // bp_weight_f, layer.h:214-227: on its way already
+            dout_s1 = fmaf(fw[q], dq[q], dout_s1);                           // bp_output_s1, layer.h:237-257
+        }
+        const float dpre_s1 = dout_s1 * s1o * (1.0f - s1o);                  // bp_preact_s1, layer.h:260-270
+        dws[16] = dpre_s1;                                                   // bp_bias_s1 accumulator, layer.h:303-314
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            dws[p] = dpre_s1 * o[p];                                         // bp_weight_s1, layer.h:272-300
+            const float dout_c1 = S.params[OFF_S1W + p] * dpre_s1;           // bp_output_c1, layer.h:319-346
+            dpc[p] = dout_c1 * (o[p] * (1.0f - o[p]));                       // bp_preact_c1, layer.h:348-369
+            bsum_c1 += dpc[p];                                               // bp_bias_c1 accumulator, layer.h:400-410
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < 17; ++p) {                                           // s1 sums: warp level now, across warps at the end
+        const float v = warp_sum(dws[p]);
+        if (lane == 0) S.red_s1[warp][p] = v;
+    }
+    if (id.worker) {
+        // bp_weight_c1, layer.h:371-395 (the /576 is applied once, below): the patch comes back from shared memory in one go
+        // (16 loads), so the FFMA block below has register operands only
+        float patch[8][8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
+            const float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
+            patch[r][0] = lo.x; patch[r][1] = lo.y; patch[r][2] = lo.z; patch[r][3] = lo.w;
+            patch[r][4] = hi.x; patch[r][5] = hi.y; patch[r][6] = hi.z; patch[r][7] = hi.w;
+        }
+        float *row = S.red + t * RED_STRIDE;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                float sacc = 0.0f;
+#pragma unroll
+                for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                    for (int oy = 0; oy < 4; ++oy) sacc = fmaf(dpc[ox * 4 + oy], patch[ox + i][oy + j], sacc);
+                row[i * 5 + j] = sacc;
+            }
+        row[25] = bsum_c1;
+    }
+    __syncthreads();                                                         // sync #3: S.red, S.red_s1 complete
+    if (t < 156) {                       // 150 c1 taps + 6 c1 bias sums: sum over the 36 windows of a map, 4 chains
+        const int mm = t < 150 ? t / 25 : t - 150;
+        const int col = t < 150 ? t % 25 : 25;
+        const float *r = S.red + (mm * 36) * RED_STRIDE + col;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 36; w += 4) {
+            s0 += r[(w + 0) * RED_STRIDE];
+            s1 += r[(w + 1) * RED_STRIDE];
+            s2 += r[(w + 2) * RED_STRIDE];
+            s3 += r[(w + 3) * RED_STRIDE];
+        }
+        const float ssum = (s0 + s1) + (s2 + s3);
+        if (t < 150) put(OFF_C1W + t, ssum * (1.0f / 576.0f));
+        else put(OFF_C1B + mm, ssum);
+    } else if (t < 173) {                // s1 taps and s1 bias sum
+        const int p = t - 156;
+        float ssum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) ssum += S.red_s1[w][p];
+        put(OFF_S1W + p, ssum);          // p == 16 lands on OFF_S1B
+    }
+}
+
 // entry p of the packed vector: w += step * g in the reference's operand order (layer.h:99, :316, :412)
 __device__ __forceinline__ float updated_entry(float w, int p, float g, float step) {
     if (p >= OFF_C1B && p < OFF_S1W) return w + step * g / 576.0f;

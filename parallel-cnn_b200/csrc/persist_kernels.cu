@@ -205,6 +205,17 @@ template <typename InT, int CS>
 __device__ __forceinline__ int step_images(FusedSmem<InT> &S, const ThreadId &id, const InT *img_base, const uint8_t *lab_base, int c, int G,
                                            int nb, int li, unsigned crank, long long *trace_row, long long *trace_row2) {
     const ChunkGate<InT> gate{&S};
+    if (nb <= G) {
+        // at most one image per CTA (batch <= grid, the usual case): the specialised single-image step; the image was
+        // prepared (landed + converted) while the CTA was waiting for the parameters
+        image_step_single(S, id, li, c < nb, PushSink<InT, CS>{&S, crank});
+        if (id.t == 0 && (trace_row || trace_row2)) {
+            const long long now = globaltimer_ns();
+            if (trace_row) trace_row[2] = now;
+            if (trace_row2) trace_row2[2] = now;
+        }
+        return c < nb ? li + 1 : li;
+    }
     Acc A;
     A.zero();
     const EvalOut ev = {nullptr, nullptr, true};

@@ -6,14 +6,16 @@ N=${N:-2}
 OUT=gpurun_out; mkdir -p $OUT
 nvidia-smi -L | head -8
 nvidia-smi topo -m 2>/dev/null | head -12 > $OUT/topo_$N.txt
-echo "== parity (pytest, world = all visible GPUs, batch 64 and 1024)"
-rm -f $OUT/mgpu_parity_n$N.log
-PCNN_MGPU_LOG_DIR=$PWD/$OUT timeout 900 python -m pytest tests/test_persist_gpu.py -m gpu -q -x -p no:cacheprovider -k data_parallel 2>&1 | tail -5
-cat $OUT/mgpu_parity_n$N.log
+if [ "${SKIP_PARITY:-0}" != "1" ]; then
+  echo "== parity (pytest, world = all visible GPUs, batch 64 and 1024)"
+  rm -f $OUT/mgpu_parity_n$N.log
+  PCNN_MGPU_LOG_DIR=$PWD/$OUT timeout 900 python -m pytest tests/test_persist_gpu.py -m gpu -q -x -p no:cacheprovider -k data_parallel 2>&1 | tail -5
+  cat $OUT/mgpu_parity_n$N.log
+fi
 for MODE in ${MODES:-persistent graph}; do
   echo "== bench N=$N mode=$MODE"
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700 + RANDOM % 200)) \
-      bench.py --gpus $N --steps ${STEPS:-2000} --warmup 100 --mode $MODE --no-cpu-baseline > $OUT/bench_n${N}_$MODE.json 2> $OUT/bench_n${N}_$MODE.err
+      bench.py --gpus $N --steps ${STEPS:-2000} --warmup ${WARMUP:-100} --mode $MODE --no-cpu-baseline > $OUT/bench_n${N}_$MODE.json 2> $OUT/bench_n${N}_$MODE.err
   echo "rc=$?"; python - <<PY
 import json
 try:
