@@ -148,6 +148,26 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 
+// Sixteen sums over the warp at once, "transposed": every round halves the number of values a lane holds instead of the
+// number of lanes a value lives in -- 15 + 1 shuffles and adds (plus selects) instead of 16 x 5.  Returns, in EVERY lane, the
+// warp-wide sum of v[(lane >> 1) & 15].  Fixed association order (deterministic).
+__device__ __forceinline__ float warp_sum16_transposed(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = (up ? v[i + 8] : v[i]) + __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 8], 16);
+    up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b[i] = (up ? a[i + 4] : a[i]) + __shfl_xor_sync(0xffffffffu, up ? a[i] : a[i + 4], 8);
+    up = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) c[i] = (up ? b[i + 2] : b[i]) + __shfl_xor_sync(0xffffffffu, up ? b[i] : b[i + 2], 4);
+    up = (lane & 2) != 0;
+    float d = (up ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, up ? c[0] : c[1], 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
 struct ThreadId {
     int t, warp, lane, m, wx, wy;
     bool worker;
@@ -490,9 +510,11 @@ __device__ __forceinline__ void image_step_single(FusedSmem<InT> &S, const Threa
     const bool work = id.worker && has_image;
     float o[16];
     float s1o = 0.0f;
-    float fcp[PCNN_F], fw[PCNN_F];
+    float fcp[16], fw[PCNN_F];          // fcp: ten partial products, padded to the sixteen of the transposed warp sum
 #pragma unroll
-    for (int q = 0; q < PCNN_F; ++q) fcp[q] = fw[q] = 0.0f;
+    for (int q = 0; q < 16; ++q) fcp[q] = 0.0f;
+#pragma unroll
+    for (int q = 0; q < PCNN_F; ++q) fw[q] = 0.0f;
 #pragma unroll
     for (int p = 0; p < 16; ++p) o[p] = 0.0f;
     const float *ip = S.imgf[buf] + (id.worker ? (4 * id.wx) * 28 + 4 * id.wy : 0);
@@ -534,10 +556,9 @@ __device__ __forceinline__ void image_step_single(FusedSmem<InT> &S, const Threa
         }
     }
     __syncwarp();
-#pragma unroll
-    for (int q = 0; q < PCNN_F; ++q) {
-        const float v = warp_sum(fcp[q]);
-        if (lane == 0) S.fc_red[warp][q] = v;
+    {
+        const float v = warp_sum16_transposed(fcp, lane);                    // lane 2q (and 2q + 1) holds output q's warp sum
+        if ((lane & 1) == 0 && (lane >> 1) < PCNN_F) S.fc_red[warp][lane >> 1] = v;
     }
     __syncthreads();                                                         // sync #2
     // f output, makeError (layer.h:91-95), vectorNorm (Main.cpp:28-34): every warp for itself, d_preact broadcast by shuffle
@@ -588,10 +609,14 @@ __device__ __forceinline__ void image_step_single(FusedSmem<InT> &S, const Threa
         }
     }
     __syncwarp();
+    {                                                                        // s1 sums: warp level now, across warps at the end
+        float d16[16];
 #pragma unroll
-    for (int p = 0; p < 17; ++p) {                                           // s1 sums: warp level now, across warps at the end
-        const float v = warp_sum(dws[p]);
-        if (lane == 0) S.red_s1[warp][p] = v;
+        for (int p = 0; p < 16; ++p) d16[p] = dws[p];
+        const float v = warp_sum16_transposed(d16, lane);
+        if ((lane & 1) == 0) S.red_s1[warp][lane >> 1] = v;
+        const float vb = warp_sum(dws[16]);
+        if (lane == 0) S.red_s1[warp][16] = vb;
     }
     if (id.worker) {
         // bp_weight_c1, layer.h:371-395 (the /576 is applied once, below): the patch comes back from shared memory in one go
