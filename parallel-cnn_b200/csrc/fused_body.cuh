@@ -21,6 +21,7 @@ template <typename InT> struct FusedSmem {
     float f_out[PCNN_F];
     float part[NT];                                  // persistent kernel: slot-phase partial sums of the owned chunk
     alignas(16) float recv[NPACK + 16];              // persistent kernel: [cluster rank][my share] gradient pieces pushed by the peers
+    float accf[PCNN_F * NT];                         // persistent kernel, several images per CTA: thread-private sums of the f-layer weight gradient
     float lut[256];                                  // u8 pixel -> fp32 (mnist.h:145 + Main.cpp:64), filled once per kernel
     int label[2];
     alignas(8) unsigned long long mbar[5];           // [0],[1]: image stages, [2]: parameters (bulk copy or peer pushes),
@@ -666,6 +667,195 @@ __device__ __forceinline__ void image_step_single(FusedSmem<InT> &S, const Threa
         for (int w = 0; w < NWARP; ++w) ssum += S.red_s1[w][p];
         put(OFF_S1W + p, ssum);          // p == 16 lands on OFF_S1B
     }
+}
+
+// Several images per CTA and step (batch > grid): the same structure as image_step_single -- whole patch in registers per
+// convolution, transposed warp sums -- with the batch sums kept where they cost least: the 25 + 1 c1 sums in registers, the
+// f-layer weight gradient in thread-private shared memory (S.accf), the s1 sums in lane-private shared memory (S.red_s1),
+// the f bias / error sums in warp 0's registers.  Images b = c, c + G, ... < nb; the first one has been prepared by the
+// caller, the others are prefetched one ahead.  Returns the advanced image counter.
+template <typename InT, typename Gate, typename Sink>
+__device__ __forceinline__ int image_steps_multi(FusedSmem<InT> &S, const ThreadId &id, const InT *img_base, const uint8_t *lab_base, int c,
+                                                 int G, int nb, int li, const Gate &gate, const Sink &put) {
+    const int t = id.t, warp = id.warp, lane = id.lane;
+    float dw_c1[25];
+#pragma unroll
+    for (int k = 0; k < 25; ++k) dw_c1[k] = 0.0f;
+    float bsum_c1 = 0.0f, gfb = 0.0f, err_acc = 0.0f;
+#pragma unroll
+    for (int q = 0; q < PCNN_F; ++q) S.accf[q * NT + t] = 0.0f;              // thread-private
+    if ((lane & 1) == 0) S.red_s1[warp][lane >> 1] = 0.0f;                   // lane-private
+    if (lane == 0) S.red_s1[warp][16] = 0.0f;
+    const float *ip_off = nullptr;
+    for (int b = c; b < nb; b += G, ++li) {
+        const int buf = li & 1;
+        if (b != c) image_prepare(S, id, li, lab_base + b);
+        __syncthreads();                                                     // sync #1: image (+ parameters) visible
+        const int bn = b + G;
+        if (t == 0 && bn < nb) {
+            const InT *nsrc = img_base + (long long)bn * PCNN_IMG;
+            gate(nsrc);
+            issue_image(S, buf ^ 1, nsrc);
+        }
+        __syncwarp();
+        float o[16];
+        float s1o = 0.0f;
+        float fcp[16], fw[PCNN_F];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) fcp[q] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < PCNN_F; ++q) fw[q] = 0.0f;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) o[p] = 0.0f;
+        const float *ip = S.imgf[buf] + (id.worker ? (4 * id.wx) * 28 + 4 * id.wy : 0);
+        ip_off = ip;
+        if (id.worker) {
+            float patch[8][8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
+                const float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
+                patch[r][0] = lo.x; patch[r][1] = lo.y; patch[r][2] = lo.z; patch[r][3] = lo.w;
+                patch[r][4] = hi.x; patch[r][5] = hi.y; patch[r][6] = hi.z; patch[r][7] = hi.w;
+            }
+            float acc[16];
+#pragma unroll
+            for (int p = 0; p < 16; ++p) acc[p] = 0.0f;
+            const float *wc = S.params + OFF_C1W + id.m * 25;
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    const float w = wc[i * 5 + j];
+#pragma unroll
+                    for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                        for (int oy = 0; oy < 4; ++oy) acc[ox * 4 + oy] = fmaf(patch[ox + i][oy + j], w, acc[ox * 4 + oy]);
+                }
+            const float bc = S.params[OFF_C1B + id.m];
+            float s1pre = 0.0f;
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                o[p] = sigmoid_fast(acc[p] + bc);
+                s1pre = fmaf(S.params[OFF_S1W + p], o[p], s1pre);
+            }
+            s1o = sigmoid_fast(s1pre + S.params[OFF_S1B]);
+#pragma unroll
+            for (int q = 0; q < PCNN_F; ++q) {
+                fw[q] = S.params[OFF_FW + q * PCNN_S1 + t];
+                fcp[q] = fw[q] * s1o;
+            }
+        }
+        __syncwarp();
+        {
+            const float v = warp_sum16_transposed(fcp, lane);
+            if ((lane & 1) == 0 && (lane >> 1) < PCNN_F) S.fc_red[warp][lane >> 1] = v;
+        }
+        __syncthreads();                                                     // sync #2
+        float dq[PCNN_F];
+        float d = 0.0f;
+        if (lane < PCNN_F) {
+            float pre = 0.0f;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) pre += S.fc_red[w][lane];
+            pre += S.params[OFF_FB + lane];
+            d = (lane == S.label[buf] ? 1.0f : 0.0f) - sigmoid_fast(pre);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < PCNN_F; ++q) dq[q] = __shfl_sync(0xffffffffu, d, q);
+        if (warp == 0) {
+            gfb += d;
+            float ss = 0.0f;
+#pragma unroll
+            for (int q = 0; q < PCNN_F; ++q) ss = fmaf(dq[q], dq[q], ss);
+            err_acc += sqrtf(ss);
+        }
+        float dpc[16], dws[16];
+        float dpre_s1 = 0.0f;
+#pragma unroll
+        for (int p = 0; p < 16; ++p) dpc[p] = dws[p] = 0.0f;
+        if (id.worker) {
+            float dout_s1 = 0.0f;
+#pragma unroll
+            for (int q = 0; q < PCNN_F; ++q) {
+                S.accf[q * NT + t] = fmaf(dq[q], s1o, S.accf[q * NT + t]);   // bp_weight_f, layer.h:214-227
+                dout_s1 = fmaf(fw[q], dq[q], dout_s1);
+            }
+            dpre_s1 = dout_s1 * s1o * (1.0f - s1o);
+#pragma unroll
+            for (int p = 0; p < 16; ++p) {
+                dws[p] = dpre_s1 * o[p];
+                const float dout_c1 = S.params[OFF_S1W + p] * dpre_s1;
+                dpc[p] = dout_c1 * (o[p] * (1.0f - o[p]));
+                bsum_c1 += dpc[p];
+            }
+        }
+        __syncwarp();
+        {
+            const float v = warp_sum16_transposed(dws, lane);
+            if ((lane & 1) == 0) S.red_s1[warp][lane >> 1] += v;
+            const float vb = warp_sum(dpre_s1);
+            if (lane == 0) S.red_s1[warp][16] += vb;
+        }
+        if (id.worker) {
+            float patch[8][8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const float4 lo = *reinterpret_cast<const float4 *>(ip + r * 28);
+                const float4 hi = *reinterpret_cast<const float4 *>(ip + r * 28 + 4);
+                patch[r][0] = lo.x; patch[r][1] = lo.y; patch[r][2] = lo.z; patch[r][3] = lo.w;
+                patch[r][4] = hi.x; patch[r][5] = hi.y; patch[r][6] = hi.z; patch[r][7] = hi.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i)
+#pragma unroll
+                for (int j = 0; j < 5; ++j) {
+                    float sacc = dw_c1[i * 5 + j];
+#pragma unroll
+                    for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                        for (int oy = 0; oy < 4; ++oy) sacc = fmaf(dpc[ox * 4 + oy], patch[ox + i][oy + j], sacc);
+                    dw_c1[i * 5 + j] = sacc;
+                }
+        }
+    }
+    (void)ip_off;
+    // ---- CTA reduction of the batch sums
+    if (id.worker) {
+#pragma unroll
+        for (int q = 0; q < PCNN_F; ++q) put(OFF_FW + q * PCNN_S1 + t, S.accf[q * NT + t]);
+        float *row = S.red + t * RED_STRIDE;
+#pragma unroll
+        for (int k = 0; k < 25; ++k) row[k] = dw_c1[k];
+        row[25] = bsum_c1;
+    }
+    if (t < PCNN_F) put(OFF_FB + t, gfb);
+    if (t == 0) put(OFF_ERR, err_acc);
+    __syncthreads();
+    if (t < 156) {
+        const int mm = t < 150 ? t / 25 : t - 150;
+        const int col = t < 150 ? t % 25 : 25;
+        const float *r = S.red + (mm * 36) * RED_STRIDE + col;
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 36; w += 4) {
+            s0 += r[(w + 0) * RED_STRIDE];
+            s1 += r[(w + 1) * RED_STRIDE];
+            s2 += r[(w + 2) * RED_STRIDE];
+            s3 += r[(w + 3) * RED_STRIDE];
+        }
+        const float ssum = (s0 + s1) + (s2 + s3);
+        if (t < 150) put(OFF_C1W + t, ssum * (1.0f / 576.0f));
+        else put(OFF_C1B + mm, ssum);
+    } else if (t < 173) {
+        const int p = t - 156;
+        float ssum = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) ssum += S.red_s1[w][p];
+        put(OFF_S1W + p, ssum);
+    }
+    return li;
 }
 
 // entry p of the packed vector: w += step * g in the reference's operand order (layer.h:99, :316, :412)

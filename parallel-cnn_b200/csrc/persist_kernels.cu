@@ -216,20 +216,12 @@ __device__ __forceinline__ int step_images(FusedSmem<InT> &S, const ThreadId &id
         }
         return c < nb ? li + 1 : li;
     }
-    Acc A;
-    A.zero();
-    const EvalOut ev = {nullptr, nullptr, true};
-    for (int b = c; b < nb; b += G, ++li) {
-        const int bn = b + G;
-        // the step's first image was prepared (landed + converted) while the CTA was waiting for the parameters
-        image_pass<InT, true>(S, id, li, lab_base + b, bn < nb ? img_base + (long long)bn * PCNN_IMG : nullptr, -1, A, ev, gate, b == c);
-    }
+    li = image_steps_multi(S, id, img_base, lab_base, c, G, nb, li, gate, PushSink<InT, CS>{&S, crank});
     if (id.t == 0 && (trace_row || trace_row2)) {
         const long long now = globaltimer_ns();
         if (trace_row) trace_row[2] = now;
         if (trace_row2) trace_row2[2] = now;
     }
-    cta_epilogue(S, id, A, PushSink<InT, CS>{&S, crank});
     return li;
 }
 
