@@ -110,8 +110,7 @@ def test_config5_shape(eng, pkg, N, H, W):
 def test_other_small_channel_shapes(eng, pkg):
     conv_case(eng, pkg, 5, 12, 30, 2, 16, 3, 5, act=0, seed=9)      # C = 2, K = 16, 3x5 taps
     conv_case(eng, pkg, 2, 33, 33, 4, 32, 5, 3, act=1, seed=10)     # C = 4, K = 32, 5x3 taps, sigmoid epilogue
-    # the second convolution of the LeNet-5-style variant: 12x12x6 -> 16 filters 5x5, sigmoid epilogue
-    conv_case(eng, pkg, 16, 12, 12, 6, 16, 5, 5, act=1, seed=12)
+    conv_case(eng, pkg, 16, 12, 12, 4, 16, 5, 5, act=1, seed=12)    # C = 4, K = 16, 5x5 taps (20 + alignment remainder <= 32)
 
 
 @pytest.mark.parametrize("shape", [(3, 28, 28, 1, 16, 5, 5, 2),      # LeNet-sized input, stride 2: 12 x 12 outputs
@@ -147,6 +146,10 @@ def test_strided_convolution(eng, pkg, shape):
 
 
 def test_plan_rejects_unsupported_shapes(eng, pkg):
+    with pytest.raises(pkg.PcnnError):
+        # the second convolution of the LeNet-5-style variant (12x12x6 -> 16 x 5x5): 5 taps x 6 channels + the 16-byte
+        # alignment remainder exceed the 32-element chunk of one filter row -- that layer runs in csrc/lenet5_kernels.cu
+        pkg.ConvPlan(eng, 4, 12, 12, 6, 16, 5, 5, np.zeros(16 * 25 * 6, np.float32))
     with pytest.raises(pkg.PcnnError):
         pkg.ConvPlan(eng, 1, 32, 32, 64, 64, 3, 3, np.zeros(64 * 9 * 64, np.float32))      # (Qt+S-1)*C > 32 for every Qt
     with pytest.raises(pkg.PcnnError):
