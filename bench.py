@@ -403,6 +403,11 @@ def run_ours(a):
     if rank == 0:
         sampler.start()
 
+    # the fp32 FMA rate of this GPU under its current clocks (the roofline's denominator), measured BEFORE the timed regions:
+    # ~15 ms of dense FFMA also takes the GPU out of its idle clock state, which a 20-step timed region (0.2 ms) would
+    # otherwise still be ramping out of
+    fp32_peak = eng.measure_fp32_peak()
+
     # ---- value: device-resident inputs
     eng.train_steps_prepare(B, K)            # instantiate the step graphs the timed call replays (host work, untimed)
     eng.train_steps(0, B, W)                 # W untimed warm-up steps
@@ -478,7 +483,6 @@ def run_ours(a):
     # ---- roofline of the dominant kernel + live fp32 peak
     line = None
     if rank == 0:
-        fp32_peak = eng.measure_fp32_peak()
         k_ms = eng.time_fused_kernel(B, max(200, min(K, 5000)))
         t_gpu_end = time.time()
         clocks = sampler.stop(t_wall0, t_gpu_end)
