@@ -29,7 +29,7 @@ template <typename InT> struct FusedSmem {
     // host-streaming gate of the persistent kernel (written and read by thread 0 only)
     const void *gate_images;
     const unsigned *gate_ready;
-    long long gate_first, gate_chunk;
+    pcnn_chunking gate_chunks;
     int *gate_abort;
     unsigned gate_tag;
     int aborted;                                     // persistent kernel: a wait of this CTA has given up; later waits return at once

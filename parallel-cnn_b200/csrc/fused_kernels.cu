@@ -603,17 +603,18 @@ static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel
     seg_samples = (seg_samples / B) * B;
     if (seg_samples < B) seg_samples = B;
     if (seg_samples > n) seg_samples = n;
-    // chunk 0: ~128 KB (at least one batch) so that the first step starts after a few microseconds of DMA; later chunks:
-    // 1/64 of the segment, between 512 KB and 16 MB (per-chunk cost: two enqueues on the host, ~2 us on the copy engine)
-    long first = (long)((128 << 10) / img_bytes);
-    first = ((first + B - 1) / B) * B;
-    if (first > seg_samples) first = seg_samples;
-    size_t cb = (size_t)seg_samples * img_bytes / 64;
-    if (cb < ((size_t)512 << 10)) cb = (size_t)512 << 10;
-    if (cb > ((size_t)16 << 20)) cb = (size_t)16 << 20;
-    long chunk = (long)(cb / img_bytes);
-    if (chunk < 1) chunk = 1;
-    const long max_chunks = 1 + (seg_samples - first + chunk - 1) / chunk;
+    // chunk 0: one batch (at least ~128 KB), then chunks doubling from ~256 KB up to 16 MB (pcnn_chunking)
+    pcnn_chunking ch;
+    ch.first = (long)((128 << 10) / img_bytes);
+    ch.first = ((ch.first + B - 1) / B) * B;
+    if (ch.first > seg_samples) ch.first = seg_samples;
+    ch.c1 = (long)((256 << 10) / img_bytes);
+    if (ch.c1 < 1) ch.c1 = 1;
+    ch.cmax = (long)(((size_t)16 << 20) / img_bytes);
+    if (ch.cmax < ch.c1) ch.cmax = ch.c1;
+    ch.kc = 0;
+    while ((ch.c1 << ch.kc) < ch.cmax && ch.kc < 16) ++ch.kc;          // sizes c1, 2 c1, ... < cmax, then cmax
+    const long max_chunks = (long)pcnn_chunk_of(ch, seg_samples > 0 ? seg_samples - 1 : 0) + 1;
     int rc;
     if ((rc = ensure_host_stream(ctx, (size_t)seg_samples * img_bytes, seg_samples, max_chunks))) return rc;
     const long total_steps = (n + B - 1) / B;
@@ -655,8 +656,7 @@ static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel
                 gate.flags = ctx->d_hs_ready;
                 gate.tag = ++ctx->hs_serial;
                 if (gate.tag == 0) gate.tag = ++ctx->hs_serial;
-                gate.first_samples = first < sn ? first : sn;
-                gate.chunk_samples = chunk;
+                gate.chunks = ch;
                 *ctx->h_hs_tag = gate.tag;   // the previous user of this word has been synchronised with (end of every launch)
                 // The kernel goes first: it sets itself up while the host enqueues the copies, and waits on the flag of a
                 // sample's chunk before it touches the sample.  Where kernel launches block the calling thread until the
@@ -670,7 +670,7 @@ static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel
                 PCNN_CUDA(cudaMemcpyAsync(ctx->d_hs_labels, host_labels + off, (size_t)sn, cudaMemcpyHostToDevice, ctx->copy_stream));
                 long k = 0;
                 for (long co = 0; co < sn; ++k) {
-                    const long cs0 = k == 0 ? gate.first_samples : chunk;
+                    const long cs0 = (long)pcnn_chunk_size(ch, k);
                     const long cs = sn - co < cs0 ? sn - co : cs0;
                     PCNN_CUDA(cudaMemcpyAsync((char *)ctx->d_hs_images + (size_t)co * img_bytes, hi + (size_t)(off + co) * img_bytes,
                                               (size_t)cs * img_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));

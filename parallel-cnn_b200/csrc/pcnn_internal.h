@@ -176,12 +176,33 @@ int pcnn_launch_reduce(pcnn_ctx *ctx, int grid_slots, int B, const pcnn_step_src
 int pcnn_launch_update(pcnn_ctx *ctx, int B, const pcnn_step_src &src, bool record_err);
 // persist_kernels.cu
 int pcnn_persist_configure(pcnn_ctx *ctx);
-// host streaming: chunk 0 holds the first `first_samples` samples, every later chunk `chunk_samples`; the samples of
-// chunk k are readable once flags[k] == tag
+// Host streaming: the staged samples are cut into chunk 0 = [0, first) (one batch: the first step starts after a few
+// microseconds of DMA), then kc chunks that double in size starting at c1 samples, then chunks of cmax samples -- short
+// calls get few, soon-available chunks, long calls amortise the per-copy cost.  The samples of chunk k are readable once
+// flags[k] == tag.  One function maps a sample to its chunk on both sides.
+struct pcnn_chunking {
+    long long first, c1, cmax;
+    int kc;
+};
+__host__ __device__ inline long long pcnn_chunk_of(const pcnn_chunking &g, long long sample) {
+    if (sample < g.first) return 0;
+    const long long r = sample - g.first;
+    const long long geo = g.c1 * ((1LL << g.kc) - 1);
+    if (r < geo) {
+        long long x = r / g.c1 + 1;
+        int lg = 0;
+        while (x >>= 1) ++lg;
+        return 1 + lg;
+    }
+    return 1 + g.kc + (r - geo) / g.cmax;
+}
+__host__ __device__ inline long long pcnn_chunk_size(const pcnn_chunking &g, long long k) {
+    return k == 0 ? g.first : (k <= g.kc ? g.c1 << (k - 1) : g.cmax);
+}
 struct pcnn_persist_gate {
     const unsigned *flags;
     unsigned tag;
-    long long first_samples, chunk_samples;
+    pcnn_chunking chunks;
 };
 // fresh bit 0: start at sample 0 / step 0 (no device-side counter read); bit 1: the error sum restarts at 0
 int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nsteps, const pcnn_persist_gate *gate = nullptr,

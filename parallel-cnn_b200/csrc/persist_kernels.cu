@@ -30,11 +30,10 @@ struct PersistArgs {
     llword *slots_ll;         // [grid][NPACK] tagged partial gradients
     llword *params_ll;        // [NPACK] tagged parameters: tag X = the parameters step X trains with
     unsigned xstep_base;      // same for the peer exchange (advances only on distributed launches)
-    // host streaming (pcnn_learn_host): sample i may be read once ready[i / ready_chunk] == ready_tag
+    // host streaming (pcnn_learn_host): sample i may be read once ready[pcnn_chunk_of(ready_chunks, i)] == ready_tag
     const unsigned *ready;
     unsigned ready_tag;
-    long long ready_first;    // samples in chunk 0 (kept short so that the first step starts early)
-    long long ready_chunk;    // samples in every later chunk
+    pcnn_chunking ready_chunks;   // sample -> chunk (pcnn_chunk_of)
     int fresh;                // bit 0: start at sample 0 / step 0 instead of the device-side counters; bit 1: err_total = 0
     float *step_err_host;     // optional mapped pinned array [nsteps]: per-step error sums written straight to the host
     double *done_host;        // optional mapped pinned {double error sum, unsigned tag}: written after the LAST step, so the
@@ -189,8 +188,7 @@ template <typename InT> struct ChunkGate {
         const unsigned *ready = S->gate_ready;
         if (!ready) return;
         const long long sample = (reinterpret_cast<const InT *>(src) - reinterpret_cast<const InT *>(S->gate_images)) / PCNN_IMG;
-        const long long first = S->gate_first;
-        const unsigned *f = ready + (sample < first ? 0 : 1 + (sample - first) / S->gate_chunk);
+        const unsigned *f = ready + pcnn_chunk_of(S->gate_chunks, sample);
         const unsigned want = S->gate_tag;
         PollGuard guard(S->gate_abort, &S->aborted);
         while (*(const volatile unsigned *)f != want)
@@ -237,8 +235,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
     if (t == 0) {
         S.gate_images = a.images;
         S.gate_ready = a.ready;
-        S.gate_chunk = a.ready_chunk;
-        S.gate_first = a.ready_first;
+        S.gate_chunks = a.ready_chunks;
         S.gate_abort = a.abort_flag;
         S.gate_tag = a.ready_tag;
         S.aborted = 0;
@@ -594,8 +591,7 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
         if (gate) {
             a.ready = gate->flags;
             a.ready_tag = gate->tag;
-            a.ready_first = gate->first_samples;
-            a.ready_chunk = gate->chunk_samples;
+            a.ready_chunks = gate->chunks;
         }
         a.fresh = fresh;
         fresh = 0;                                                 // a split longer than one launch continues
