@@ -114,7 +114,8 @@ struct pcnn_ctx {
     int persist_cluster_cap = 0;            // co-resident CTAs when launched as clusters of 8
     bool persist_no_coop = false;           // the driver refused cooperative + cluster launches
     int persist_force_cluster = 0;          // > 0: cap the cluster size (A/B measurements through pcnn_persist_tune)
-    int persist_last_cluster = 0, persist_last_grid = 0;
+    int persist_last_cluster = 0, persist_last_grid = 0, persist_last_direct = 0;
+    bool persist_no_direct = false;         // measurement knob: keep the two-stage exchange on 2..4 GPUs
     int *d_abort = nullptr;                 // set by a spin loop that ran out of budget
     long long *d_trace = nullptr;           // optional phase timestamps of the persistent kernel (pcnn_persist_trace)
     unsigned p2p_step_id = 0;               // distributed steps issued since pcnn_p2p_attach (tags of the peer exchange)

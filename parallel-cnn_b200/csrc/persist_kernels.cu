@@ -9,6 +9,11 @@ using namespace pcnn_fused;
 
 namespace {
 
+constexpr int XS_MAXC = 40;          // clusters per rank the direct exchange has room for (a B200 holds 33 clusters of 8)
+constexpr int PCNN_DIRECT_MAX_WORLD = 2;   // measured: 2 GPUs 9.86 vs 10.95 us per step; 4 GPUs 11.27 vs 11.14 (no gain: 3 x 0.6 MB of stores per step and GPU)
+static size_t p2p_inbox_bytes() { return (size_t)2 * PCNN_MAX_PEERS * NPACK * sizeof(uint2); }
+static size_t p2p_xslots_bytes() { return (size_t)2 * PCNN_MAX_PEERS * XS_MAXC * NPACK * sizeof(unsigned long long); }
+
 struct PersistArgs {
     const void *images;
     const uint8_t *labels;
@@ -30,6 +35,12 @@ struct PersistArgs {
     llword *slots_ll;         // [grid][NPACK] tagged partial gradients
     llword *params_ll;        // [NPACK] tagged parameters: tag X = the parameters step X trains with
     unsigned xstep_base;      // same for the peer exchange (advances only on distributed launches)
+    // direct exchange (2 GPUs): every cluster's share owner also stores its share into the peers' copies of this array,
+    // [2 parities][PCNN_MAX_PEERS source ranks][XS_MAXC clusters][NPACK] tagged words in IPC-mapped memory; the owners then
+    // gather ranks x clusters slots in one go and the separate exchange hop disappears
+    llword *xslots;
+    llword *peer_xslots[PCNN_MAX_PEERS];
+    int direct;
     // host streaming (pcnn_learn_host): sample i may be read once ready[pcnn_chunk_of(ready_chunks, i)] == ready_tag
     const unsigned *ready;
     unsigned ready_tag;
@@ -50,6 +61,16 @@ __device__ __forceinline__ long long globaltimer_ns() {
 // {value, step id} words of the peer exchange: one 8-byte volatile access each way (bypasses L1, single-copy atomic)
 __device__ __forceinline__ void st_ll(uint2 *p, float value, unsigned id) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(value)), "r"(id) : "memory");
+}
+// tagged 64-bit words in PEER-visible memory (system scope: the writer is another GPU)
+__device__ __forceinline__ void ll_store_sys(llword *p, float v, unsigned tag) {
+    asm volatile("{ .reg .b64 t; mov.b64 t, {%1, %2}; st.relaxed.sys.global.u64 [%0], t; }" ::"l"(p), "r"(__float_as_uint(v)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ void ll_load_sys(const llword *p, float &v, unsigned &tag) {
+    unsigned lo;
+    asm volatile("{ .reg .b64 t; ld.relaxed.sys.global.u64 t, [%2]; mov.b64 {%0, %1}, t; }" : "=r"(lo), "=r"(tag) : "l"(p) : "memory");
+    v = __uint_as_float(lo);
 }
 __device__ __forceinline__ uint2 ld_ll(const uint2 *p) {
     uint2 v;
@@ -252,7 +273,8 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
     const int cnt = e0 >= NPACK ? 0 : (e0 + chunk > NPACK ? NPACK - e0 : chunk);
     const int PH = chunk >= NT ? 1 : NT / chunk;         // slot phases when the chunk is narrower than the CTA
     constexpr int KB = 8;                                // slot words one thread keeps in flight
-    const int PHG = PH < (NC + KB - 1) / KB ? PH : (NC + KB - 1) / KB;   // phases in use: thread (e, ph) adds slots ph, ph + PHG, ...
+    const int NV = a.direct ? NC * a.world : NC;         // slots an owner gathers: clusters (x ranks with the direct exchange)
+    const int PHG = PH < (NV + KB - 1) / KB ? PH : (NV + KB - 1) / KB;   // phases in use: thread (e, ph) adds slots ph, ph + PHG, ...
 
     long long cursor = (a.fresh & 1) ? 0 : *a.cursor;
     const int step_idx0 = (a.fresh & 1) ? 0 : *a.step_idx;
@@ -329,6 +351,12 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
 #pragma unroll
                 for (int q = 0; q < CS; ++q) g += S.recv[q * Share<CS>::SH + i];
                 ll_store(cslot + my_sb + i, g, tag);
+                if (a.direct) {          // the peers' owners gather this cluster's share straight from their own memory
+                    const unsigned xt = a.xstep_base + (unsigned)s + 1u;
+                    const long long off = ((((long long)(xt & 1u) * PCNN_MAX_PEERS + a.rank) * XS_MAXC + (CS == 1 ? c : (int)cluster_idx())) * NPACK) + my_sb + i;
+                    for (int r = 0; r < a.world; ++r)
+                        if (r != a.rank) ll_store_sys(a.peer_xslots[r] + off, g, xt);
+                }
             }
         }
         PCNN_TRACE2(3);
@@ -353,7 +381,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         const unsigned xtag = a.xstep_base + (unsigned)s + 1u;
         // entry p: local sum g, parameter value before the step w_old; returns the updated parameter
         auto finalize = [&](int p, float g, float w_old) -> float {
-            if (a.world > 1) {
+            if (a.world > 1 && !a.direct) {
                 // "low-latency" push: every 8-byte inbox word carries {value, step id}; one NVLink one-way latency per step.
                 // Every polling round then requests the words of ALL ranks still missing at once; the ranks' values are
                 // added in rank order, so all GPUs compute bit-identical sums.
@@ -402,24 +430,39 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
             const int e = t % chunk, ph = t / chunk;
             float sum = 0.0f;
             if (e < cnt && ph < PHG) {
-                const llword *sp = a.slots_ll + e0 + e;
+                // virtual slot v = (source rank, cluster): this GPU's own clusters live in slots_ll (local tag), the peers' in
+                // xslots (exchange tag); every GPU adds them in the same (rank, cluster) order -> bit-identical replicas
+                const int par = (int)(xtag & 1u);
+                auto slot_word = [&](int v, const llword *&ptr, unsigned &want, bool &remote) {
+                    const int q = v / NC, k = v - q * NC;
+                    remote = a.direct && q != a.rank;
+                    ptr = remote ? a.xslots + ((((long long)par * PCNN_MAX_PEERS + q) * XS_MAXC + k) * NPACK) + e0 + e
+                                 : a.slots_ll + (long long)k * NPACK + e0 + e;
+                    want = remote ? xtag : tag;
+                };
                 PollGuard guard(a.abort_flag, &S.aborted);
-                for (int k0 = ph; k0 < NC; k0 += KB * PHG) {
+                for (int k0 = ph; k0 < NV; k0 += KB * PHG) {
                     float v[KB];
                     unsigned pend = 0;
 #pragma unroll
                     for (int u = 0; u < KB; ++u) {
                         v[u] = 0.0f;
-                        if (k0 + u * PHG < NC) pend |= 1u << u;
+                        if (k0 + u * PHG < NV) pend |= 1u << u;
                     }
                     while (pend) {
-                        unsigned g[KB];
+                        unsigned g[KB], want[KB];
 #pragma unroll
                         for (int u = 0; u < KB; ++u)
-                            if ((pend >> u) & 1u) ll_load(sp + (long long)(k0 + u * PHG) * NPACK, v[u], g[u]);
+                            if ((pend >> u) & 1u) {
+                                const llword *ptr;
+                                bool remote;
+                                slot_word(k0 + u * PHG, ptr, want[u], remote);
+                                if (remote) ll_load_sys(ptr, v[u], g[u]);
+                                else ll_load(ptr, v[u], g[u]);
+                            }
 #pragma unroll
                         for (int u = 0; u < KB; ++u)
-                            if (((pend >> u) & 1u) && g[u] == tag) pend &= ~(1u << u);
+                            if (((pend >> u) & 1u) && g[u] == want[u]) pend &= ~(1u << u);
                         if (pend && guard.expired(1)) break;
                     }
 #pragma unroll
@@ -578,7 +621,11 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
         a.rank_local = s.rank_local ? 1 : 0;
         a.dt = ctx->lr;
         a.inbox = ctx->p2p_inbox;
-        for (int q = 0; q < PCNN_MAX_PEERS; ++q) a.peer_inbox[q] = ctx->p2p_peer_inbox[q];
+        for (int q = 0; q < PCNN_MAX_PEERS; ++q) {
+            a.peer_inbox[q] = ctx->p2p_peer_inbox[q];
+            a.peer_xslots[q] = ctx->p2p_peer_inbox[q] ? reinterpret_cast<llword *>(reinterpret_cast<char *>(ctx->p2p_peer_inbox[q]) + p2p_inbox_bytes()) : nullptr;
+        }
+        a.xslots = ctx->p2p_inbox ? reinterpret_cast<llword *>(reinterpret_cast<char *>(ctx->p2p_inbox) + p2p_inbox_bytes()) : nullptr;
         a.trace = ctx->d_trace;
         a.slots_ll = ctx->d_slots_ll;
         a.params_ll = ctx->d_params_ll;
@@ -607,6 +654,12 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
         {
             int grid = 0, cs = 1;
             persist_geometry(ctx, B, &grid, &cs);
+            // 2 GPUs: the cluster shares go straight into the peer's memory and the owners gather ranks x clusters slots (one
+            // NVLink hop replaces an L2 hop + the separate exchange: 9.86 vs 10.95 us per step).  With more GPUs the per-step
+            // NVLink volume of that scheme ((N - 1) x 0.6 MB per GPU) costs what it saves (4 GPUs: 11.27 vs 11.14 us) and the
+            // owners exchange their 9.4 KB of sums instead
+            a.direct = (ctx->world >= 2 && ctx->world <= PCNN_DIRECT_MAX_WORLD && cs > 1 && grid / cs <= XS_MAXC && grid > 16 &&
+                        !ctx->persist_no_direct) ? 1 : 0;
             const void *fn;
             if (cs > 1)
                 fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist<uint8_t, PERSIST_CS> : (const void *)k_train_persist<float, PERSIST_CS>;
@@ -647,6 +700,7 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
             }
             ctx->persist_last_cluster = cs;
             ctx->persist_last_grid = grid;
+            ctx->persist_last_direct = a.direct;
         }
         if (e != cudaSuccess) return pcnn_fail_cuda(e, "launch of k_train_persist", __FILE__, __LINE__);
         ctx->launches += 1;
@@ -673,7 +727,7 @@ int pcnn_persist_check(pcnn_ctx *ctx) {
 
 // ------------------------------------------------------------------------------------------ peer memory plumbing
 struct p2p_layout {
-    static size_t inbox_bytes() { return (size_t)2 * PCNN_MAX_PEERS * NPACK * sizeof(uint2); }
+    static size_t inbox_bytes() { return p2p_inbox_bytes() + p2p_xslots_bytes(); }      // everything a peer may write into
 };
 
 extern "C" int pcnn_p2p_export(pcnn_ctx *ctx, void *handle_out, size_t *handle_bytes) {
@@ -774,14 +828,16 @@ extern "C" int pcnn_persist_info(pcnn_ctx *ctx, int *out6) {
     out6[2] = ctx->persist_cap;
     out6[3] = ctx->persist_cluster_cap;
     out6[4] = PERSIST_CS;
-    out6[5] = ctx->persist_no_coop ? 0 : 1;
+    out6[5] = (ctx->persist_no_coop ? 0 : 1) | (ctx->persist_last_direct ? 2 : 0);
     return PCNN_OK;
 }
 
 extern "C" int pcnn_persist_tune(pcnn_ctx *ctx, int max_cluster) {
     PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_persist_tune: ctx is NULL");
-    PCNN_REQUIRE(max_cluster >= 0 && max_cluster <= 7, PCNN_ERR_ARG,
-                 "pcnn_persist_tune: bit mask of 1 (no clusters), 2 (clusters without the cooperative attribute), 4 (host copies before the launch)");
+    PCNN_REQUIRE(max_cluster >= 0 && max_cluster <= 15, PCNN_ERR_ARG,
+                 "pcnn_persist_tune: bit mask of 1 (no clusters), 2 (clusters without the cooperative attribute), 4 (host copies before the "
+                 "launch), 8 (two-stage exchange also on 2..4 GPUs)");
+    ctx->persist_no_direct = (max_cluster & 8) != 0;
     ctx->persist_force_cluster = (max_cluster & 1) ? 1 : 0;
     if (max_cluster & 2) ctx->persist_no_coop = true;
     if (max_cluster & 4) ctx->hs_copies_first = true;
