@@ -15,11 +15,11 @@
 // conv_dgrad_tc.cu
 bool pcnn_conv_dgrad_rows_ok(int N, int H, int W, int C, int K, int R, int S, const void *dy);
 int pcnn_conv_dgrad_rows(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f32_dev, void *dx_bf16, int N, int H, int W, int C, int K,
-                         int R, int S, int row_pitch, int image_rows);
+                         int R, int S, int row_pitch, int image_rows, int dy_channels = 0);
 // conv_wgrad_tc.cu
 bool pcnn_conv_wgrad_rows_ok(int N, int H, int W, int C, int K, int R, int S, int row_pitch, const void *x, const void *dy);
 int pcnn_conv_wgrad_rows(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16, float *dw_f32, int N, int H, int W, int C, int K,
-                         int R, int S, int row_pitch, int image_rows);
+                         int R, int S, int row_pitch, int image_rows, int dy_channels = 0);
 void pcnn_conv_dgrad_rows_info(int H, int W, int C, int K, int R, int S, int *out4);
 void pcnn_conv_wgrad_rows_info(int H, int W, int C, int K, int R, int S, int *out4);
 
@@ -113,6 +113,59 @@ __global__ void __launch_bounds__(256) k_conv_dgrad(const __nv_bfloat16 *__restr
     }
 }
 
+// dy [rows][K] -> [rows][Kp] bf16 with zero filter channels K..Kp-1 (the padded tensor-core path below)
+__global__ void __launch_bounds__(256) k_pad_channels_bf16(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long rows,
+                                                           int K, int Kp) {
+    const long total = rows * (Kp / 8);                       // 16-byte pieces of the destination
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+        const long r = i / (Kp / 8);
+        const int k0 = (int)(i % (Kp / 8)) * 8;
+        __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = k0 + u < K ? src[r * K + k0 + u] : __float2bfloat16_rn(0.0f);
+        *reinterpret_cast<uint4 *>(dst + r * Kp + k0) = *reinterpret_cast<const uint4 *>(v);
+    }
+}
+// filters [K][RSC] fp32 -> [Kp][RSC] with zero filters K..Kp-1
+__global__ void k_pad_filters_f32(const float *__restrict__ src, float *__restrict__ dst, int K, int Kp, int rsc) {
+    const int total = Kp * rsc;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) dst[i] = i < K * rsc ? src[i] : 0.0f;
+}
+
+// second grow-only device scratch (the tensor-core kernels use the first one themselves while they read this one)
+int scratch2(pcnn_ctx *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->scratch2_bytes) {
+        PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->scratch2) PCNN_CUDA(cudaFree(ctx->scratch2));
+        ctx->scratch2 = nullptr;
+        ctx->scratch2_bytes = 0;
+        const size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        PCNN_CUDA(cudaMalloc(&ctx->scratch2, want));
+        ctx->scratch2_bytes = want;
+    }
+    *out = ctx->scratch2;
+    return PCNN_OK;
+}
+
+// Filter counts that are not a multiple of 64 (LeNet's own 6, a C3-style 16, ...): pad the filter dimension of dy with zero
+// channels up to the next multiple of 64 and run the 64-filter tensor-core kernels -- one extra pass that writes Kp / K times the
+// bytes of dy, after which the kernel streams the padded tensor: roughly K / (2 Kp) of the roofline of the dense case (K = 32:
+// a quarter, K = 6: a twentieth), still 5-25 x the FMA-pipe reference kernels.
+int pad_dy(pcnn_ctx *ctx, const void *dy_bf16, long rows, int K, int Kp, size_t extra_bytes, __nv_bfloat16 **dyp, void **extra) {
+    const size_t dy_bytes = ((size_t)rows * Kp * 2 + 255) & ~(size_t)255;
+    void *base = nullptr;
+    int rc = scratch2(ctx, dy_bytes + extra_bytes, &base);
+    if (rc) return rc;
+    *dyp = reinterpret_cast<__nv_bfloat16 *>(base);
+    if (extra) *extra = reinterpret_cast<char *>(base) + dy_bytes;
+    const long pieces = rows * (Kp / 8);
+    long blocks = (pieces + 255) / 256;
+    if (blocks > (long)ctx->sm_count * 16) blocks = (long)ctx->sm_count * 16;
+    k_pad_channels_bf16<<<(int)blocks, 256, 0, ctx->stream>>>(reinterpret_cast<const __nv_bfloat16 *>(dy_bf16), *dyp, rows, K, Kp);
+    PCNN_CHECK_LAUNCH(ctx);
+    return PCNN_OK;
+}
+
 int check_shape(const char *fn, int N, int H, int W, int C, int K, int R, int S, int row_pitch, int image_rows, ConvShape *out) {
     PCNN_REQUIRE(N > 0 && C > 0 && K > 0 && R > 0 && S > 0 && H >= R && W >= S, PCNN_ERR_ARG, "%s: bad shape", fn);
     if (row_pitch <= 0) row_pitch = W * C;
@@ -132,8 +185,30 @@ extern "C" int pcnn_conv_wgrad(pcnn_ctx *ctx, const void *x_bf16, const void *dy
     int rc = check_shape("pcnn_conv_wgrad", N, H, W, C, K, R, S, row_pitch, image_rows, &s);
     if (rc) return rc;
     if (ctx->conv_bwd_path == PCNN_CONV_BWD_TENSOR) {
+        const int Kp = (K + 63) / 64 * 64;
+        if (K % 64 && Kp <= 256 && pcnn_conv_wgrad_rows_ok(N, H, W, C, Kp, R, S, s.row_pitch, x_bf16, nullptr)) {
+            pcnn_device_guard g(ctx->device);
+            __nv_bfloat16 *dyp = nullptr;
+            void *dwp = nullptr;
+            const int rsc = R * S * C;
+            // K a multiple of 8 (16-byte pixel pitch) and 16-byte aligned: dy is read in place, the TMA zero-fills filters
+            // K..63 of every box; otherwise (LeNet's 6 filters) one pass builds a zero-padded copy first
+            const bool in_place = K % 8 == 0 && ((uintptr_t)dy_bf16 & 15) == 0;
+            if (in_place) {
+                void *base = nullptr;
+                if ((rc = scratch2(ctx, (size_t)Kp * rsc * sizeof(float), &base))) return rc;
+                dwp = base;
+            } else if ((rc = pad_dy(ctx, dy_bf16, (long)N * s.P * s.Q, K, Kp, (size_t)Kp * rsc * sizeof(float), &dyp, &dwp))) {
+                return rc;
+            }
+            if ((rc = pcnn_conv_wgrad_rows(ctx, x_bf16, in_place ? dy_bf16 : dyp, reinterpret_cast<float *>(dwp), N, H, W, C, Kp, R, S,
+                                           s.row_pitch, s.image_rows, in_place ? K : 0)))
+                return rc;
+            PCNN_CUDA(cudaMemcpyAsync(dw_f32, dwp, (size_t)K * rsc * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));   // filters 0..K-1
+            return PCNN_OK;
+        }
         PCNN_REQUIRE(pcnn_conv_wgrad_rows_ok(N, H, W, C, K, R, S, s.row_pitch, x_bf16, dy_bf16), PCNN_ERR_ARG,
-                     "pcnn_conv_wgrad: no tensor-core kernel for C = %d, K = %d, %dx%d taps (needs K = 64/128/192/256, (RB + R - 1) * S * C <= 64, "
+                     "pcnn_conv_wgrad: no tensor-core kernel for C = %d, K = %d, %dx%d taps (needs K <= 256 -- padded to a multiple of 64 --, (RB + R - 1) * S * C <= 64, "
                      "16-byte aligned operands); the FMA-pipe reference kernels (~1 %% of the HBM roofline) must be selected explicitly with "
                      "pcnn_conv_bwd_select(ctx, PCNN_CONV_BWD_REFERENCE)", C, K, R, S);
         return pcnn_conv_wgrad_rows(ctx, x_bf16, dy_bf16, dw_f32, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
@@ -160,8 +235,27 @@ extern "C" int pcnn_conv_dgrad(pcnn_ctx *ctx, const void *dy_bf16, const float *
     int rc = check_shape("pcnn_conv_dgrad", N, H, W, C, K, R, S, row_pitch, image_rows, &s);
     if (rc) return rc;
     if (ctx->conv_bwd_path == PCNN_CONV_BWD_TENSOR) {
+        const int Kp = (K + 63) / 64 * 64;
+        if (K % 64 && Kp <= 256 && pcnn_conv_dgrad_rows_ok(N, H, W, C, Kp, R, S, nullptr)) {
+            pcnn_device_guard g(ctx->device);
+            __nv_bfloat16 *dyp = nullptr;
+            void *fp = nullptr;
+            const int rsc = R * S * C;
+            const bool in_place = K % 8 == 0 && ((uintptr_t)dy_bf16 & 15) == 0;      // see pcnn_conv_wgrad
+            if (in_place) {
+                void *base = nullptr;
+                if ((rc = scratch2(ctx, (size_t)Kp * rsc * sizeof(float), &base))) return rc;
+                fp = base;
+            } else if ((rc = pad_dy(ctx, dy_bf16, (long)N * s.P * s.Q, K, Kp, (size_t)Kp * rsc * sizeof(float), &dyp, &fp))) {
+                return rc;
+            }
+            k_pad_filters_f32<<<(Kp * rsc + 255) / 256, 256, 0, ctx->stream>>>(filt_f32_dev, reinterpret_cast<float *>(fp), K, Kp, rsc);
+            PCNN_CHECK_LAUNCH(ctx);
+            return pcnn_conv_dgrad_rows(ctx, in_place ? dy_bf16 : dyp, reinterpret_cast<const float *>(fp), dx_bf16, N, H, W, C, Kp, R, S,
+                                        s.row_pitch, s.image_rows, in_place ? K : 0);
+        }
         PCNN_REQUIRE(pcnn_conv_dgrad_rows_ok(N, H, W, C, K, R, S, dy_bf16), PCNN_ERR_ARG,
-                     "pcnn_conv_dgrad: no tensor-core kernel for C = %d, K = %d, %dx%d taps (needs K = 64/128/192/256 and 3x3 taps with C in "
+                     "pcnn_conv_dgrad: no tensor-core kernel for C = %d, K = %d, %dx%d taps (needs K <= 256 -- padded to a multiple of 64 -- and 3x3 taps with C in "
                      "{1,2,3,4,8}, 5x5 with C in {1,3} or 7x7 with C = 1); the FMA-pipe reference kernels (~1 %% of the HBM roofline) must be "
                      "selected explicitly with pcnn_conv_bwd_select(ctx, PCNN_CONV_BWD_REFERENCE)", C, K, R, S);
         return pcnn_conv_dgrad_rows(ctx, dy_bf16, filt_f32_dev, dx_bf16, N, H, W, C, K, R, S, s.row_pitch, s.image_rows);
@@ -261,10 +355,11 @@ extern "C" int pcnn_conv_bwd_plan_info(int N, int H, int W, int C, int K, int R,
     PCNN_REQUIRE(out9 && N > 0 && H >= R && W >= S && C > 0 && K > 0 && R > 0 && S > 0, PCNN_ERR_ARG, "pcnn_conv_bwd_plan_info: bad argument");
     for (int i = 0; i < 9; ++i) out9[i] = 0;
     const void *aligned = reinterpret_cast<const void *>((uintptr_t)256);
-    if (pcnn_conv_wgrad_rows_ok(N, H, W, C, K, R, S, 8, aligned, aligned)) pcnn_conv_wgrad_rows_info(H, W, C, K, R, S, out9);
-    if (pcnn_conv_dgrad_rows_ok(N, H, W, C, K, R, S, aligned)) {
+    const int Kp = (K + 63) / 64 * 64;          // filter counts are zero-padded to a multiple of 64 (pcnn_conv_wgrad / dgrad)
+    if (pcnn_conv_wgrad_rows_ok(N, H, W, C, Kp, R, S, 8, aligned, aligned)) pcnn_conv_wgrad_rows_info(H, W, C, Kp, R, S, out9);
+    if (pcnn_conv_dgrad_rows_ok(N, H, W, C, Kp, R, S, aligned)) {
         out9[4] = 1;
-        pcnn_conv_dgrad_rows_info(H, W, C, K, R, S, out9 + 5);
+        pcnn_conv_dgrad_rows_info(H, W, C, Kp, R, S, out9 + 5);
     }
     return PCNN_OK;
 }

@@ -316,8 +316,10 @@ void pcnn_conv_dgrad_rows_info(int H, int W, int C, int K, int R, int S, int *ou
     (void)H;
 }
 
+// dy_channels: as for pcnn_conv_wgrad_rows (filters dy really holds; the TMA zero-fills the rest of a 64-channel box)
 int pcnn_conv_dgrad_rows(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f32_dev, void *dx_bf16, int N, int H, int W, int C, int K,
-                         int R, int S, int row_pitch, int image_rows) {
+                         int R, int S, int row_pitch, int image_rows, int dy_channels) {
+    const uint64_t KD = dy_channels > 0 ? (uint64_t)dy_channels : (uint64_t)K;
     pcnn_device_guard guard(ctx->device);
     const Geometry g = geometry(R, S, C);
     Dgrad2Params p;
@@ -351,8 +353,8 @@ int pcnn_conv_dgrad_rows(pcnn_ctx *ctx, const void *dy_bf16, const float *filt_f
 
     CUtensorMap map_dy, map_b;
     {
-        const uint64_t dims[3] = {(uint64_t)K, (uint64_t)p.Q, (uint64_t)N * p.P};
-        const uint64_t str[2] = {(uint64_t)K * 2, (uint64_t)p.Q * K * 2};
+        const uint64_t dims[3] = {KD, (uint64_t)p.Q, (uint64_t)N * p.P};
+        const uint64_t str[2] = {KD * 2, (uint64_t)p.Q * KD * 2};
         const uint32_t box[3] = {64, (uint32_t)p.bp, 1};
         if ((rc = make_map_bf16(&map_dy, const_cast<void *>(dy_bf16), 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B)))

@@ -322,8 +322,11 @@ void pcnn_conv_wgrad_rows_info(int H, int W, int C, int K, int R, int S, int *ou
     out4[0] = pl.ok ? 1 : 0; out4[1] = pl.RB; out4[2] = pl.PC; out4[3] = pl.stages;
 }
 
+// dy_channels: filters dy really holds per pixel (<= K, multiple of 8: 16-byte pixel pitch); the TMA boxes stay 64 channels
+// wide and the hardware fills channels dy_channels..63 of a box with zeros, so a 16- or 32-filter gradient needs no padded copy
 int pcnn_conv_wgrad_rows(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16, float *dw_f32, int N, int H, int W, int C, int K,
-                         int R, int S, int row_pitch, int image_rows) {
+                         int R, int S, int row_pitch, int image_rows, int dy_channels) {
+    const uint64_t KD = dy_channels > 0 ? (uint64_t)dy_channels : (uint64_t)K;
     pcnn_device_guard g(ctx->device);
     const int P = H - R + 1, Q = W - S + 1;
     const Plan pl = plan_for(P, Q, C, R, S, K / 64);
@@ -349,8 +352,8 @@ int pcnn_conv_wgrad_rows(pcnn_ctx *ctx, const void *x_bf16, const void *dy_bf16,
     if (rc) return rc;
     CUtensorMap map_dy;
     {
-        const uint64_t dims[4] = {(uint64_t)K, (uint64_t)Q, (uint64_t)P, (uint64_t)N};
-        const uint64_t str[3] = {(uint64_t)K * 2, (uint64_t)Q * K * 2, (uint64_t)P * Q * K * 2};
+        const uint64_t dims[4] = {KD, (uint64_t)Q, (uint64_t)P, (uint64_t)N};
+        const uint64_t str[3] = {KD * 2, (uint64_t)Q * KD * 2, (uint64_t)P * Q * KD * 2};
         const uint32_t box[4] = {64, (uint32_t)p.PC, (uint32_t)p.RB, 1};
         if ((rc = make_map_bf16(&map_dy, const_cast<void *>(dy_bf16), 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B)))

@@ -112,6 +112,7 @@ extern "C" int pcnn_destroy(pcnn_ctx *ctx) {
     pcnn_p2p_detach(ctx);
     if (ctx->p2p_base) cudaFree(ctx->p2p_base);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->scratch2) cudaFree(ctx->scratch2);
     if (ctx->d_trace) cudaFree(ctx->d_trace);
     if (ctx->d_hs_images) cudaFree(ctx->d_hs_images);
     if (ctx->d_hs_labels) cudaFree(ctx->d_hs_labels);

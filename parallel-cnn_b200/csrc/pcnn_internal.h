@@ -131,6 +131,8 @@ struct pcnn_ctx {
     // grow-only device scratch of the convolution backward passes (partial sums, filter variants); stream-ordered reuse
     void *scratch = nullptr;
     size_t scratch_bytes = 0;
+    void *scratch2 = nullptr;               // padded operands of the convolution backward passes (conv_bwd.cu)
+    size_t scratch2_bytes = 0;
 
     int conv_bwd_path = PCNN_CONV_BWD_TENSOR;   // pcnn_conv_bwd_select
 

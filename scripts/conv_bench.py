@@ -87,6 +87,9 @@ def run_bwd(name, N, H, W, C, K, R, S, iters):
 if only in ("all", "bwd"):
     for N in (8, 32, 128):
         run_bwd("224x224x3->64x3x3 bf16 (config 5)", N, 224, 224, 3, 64, 3, 3, 10)
+if only == "bwdpad":                                                   # filter counts padded to 64: 32 filters, and LeNet's own 6
+    run_bwd("224x224x3->32x3x3 bf16 (padded to 64 filters)", 128, 224, 224, 3, 32, 3, 3, 10)
+    run_bwd("224x224x3->16x3x3 bf16 (padded to 64 filters)", 128, 224, 224, 3, 16, 3, 3, 10)
 if only == "bwdk128":                                                  # 128 filters: two 64-filter groups per dy row
     run_bwd("224x224x3->128x3x3 bf16", 64, 224, 224, 3, 128, 3, 3, 10)
 if only == "bwd128":                                                   # the profiler's target: few launches

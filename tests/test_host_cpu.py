@@ -166,7 +166,7 @@ def test_data_parallel_two_ranks_equal_single_process_gloo():
 
 def test_conv_backward_tile_planning_is_host_logic(pkg):
     """pcnn_conv_bwd_plan_info needs no GPU: the tile shapes DESIGN.md 3.7 quotes for BASELINE config 5, and the shapes that must
-    fall back to the FMA-pipe kernels."""
+    are refused (the FMA-pipe reference kernels run only after pcnn_conv_bwd_select)."""
     import ctypes as C
 
     def info(*shape):
@@ -180,7 +180,9 @@ def test_conv_backward_tile_planning_is_host_logic(pkg):
     assert cfg5[8] >= 8
     k128 = info(4, 64, 64, 3, 128, 3, 3)
     assert k128[0] == 1 and k128[1] <= 2 and k128[4] == 1          # N = RB * 128 <= 256
-    assert info(4, 28, 28, 1, 6, 5, 5)[0] == 0 and info(4, 28, 28, 1, 6, 5, 5)[4] == 0      # LeNet c1 (6 filters): FMA-pipe kernels
+    lenet = info(4, 28, 28, 1, 6, 5, 5)          # LeNet c1: 6 filters are zero-padded to 64 and run on the tensor-core kernels
+    assert lenet[0] == 1 and lenet[4] == 1        # (given a row pitch that is a multiple of 8 elements)
+    assert info(1, 32, 32, 3, 320, 3, 3)[0] == 0 and info(1, 32, 32, 3, 320, 3, 3)[4] == 0   # more than 256 filters: refused
     assert info(1, 32, 32, 3, 64, 5, 5)[0] == 0 and info(1, 32, 32, 3, 64, 5, 5)[4] == 1    # 5x5x3: 75 Hankel rows > 64
 
 
