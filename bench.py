@@ -450,6 +450,29 @@ def run_ours(a):
         e2e_s = float(t.item())
     e2e_val = n_e2e * world / e2e_s
     barrier()
+    # the host->device link as this box gives it (pinned memory, one copy, CUDA events): the ceiling of ANY end-to-end number,
+    # because every step needs B x 785 bytes across it.  Measured for 64 MB and for exactly the bytes the e2e call moved.
+    link = None
+    if rank == 0:
+        def h2d_gbps(nbytes):
+            src = torch.empty((nbytes,), dtype=torch.uint8, pin_memory=True)
+            dst = torch.empty((nbytes,), dtype=torch.uint8, device="cuda")
+            best = 0.0
+            for _ in range(4):
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(stream)
+                dst.copy_(src, non_blocking=True)
+                c1.record(stream)
+                torch.cuda.synchronize()
+                best = max(best, nbytes / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+            return best
+        big, same = h2d_gbps(64 << 20), h2d_gbps(n_e2e * 785)
+        bound = same * 1e9 / 785.0 * world
+        link = {"h2d_GBps_64MB": big, "h2d_GBps_same_bytes_one_copy": same, "link_bound_images_per_s": bound,
+                "e2e_frac_of_link_bound": e2e_val / bound,
+                "note": "one cudaMemcpyAsync of the e2e call's input bytes, nothing else: no training step can start before "
+                        "its pixels have crossed this link"}
+    barrier()
 
     # ---- BASELINE.json configs[3]: 1024 images per GPU (weak) and a fixed global batch of 8192 (strong)
     b1024 = None
@@ -543,7 +566,8 @@ def run_ours(a):
                        "l2": f"inputs larger than L2: steps walk a {n_data}-image ({n_data * 784 / 1e6:.0f} MB) device-resident set",
                        "update": "w += (dt / global_batch) * sum_b g_b, dt = 0.1 (equals the reference at batch 1)"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * 785 * world,
-                    "d2h_bytes_per_step": 4 * world, "steps": K2, "api": "Engine.learn_host (pcnn_learn_host), pinned host u8"},
+                    "d2h_bytes_per_step": 4 * world, "steps": K2, "api": "Engine.learn_host (pcnn_learn_host), pinned host u8",
+                    "link": link},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "ref_gpu_baseline": ref_gpu, "clocks": clocks,
             "parity": parity, "batch1024": b1024, "phase_trace": phases, "conv": conv,
         }

@@ -211,7 +211,9 @@ int pcnn_set_step_mode(pcnn_ctx *ctx, int mode);
  * cooperative attribute (profilers that re-issue cooperative launches drop the cluster dimension); bit 2 makes
  * pcnn_learn_host enqueue its host copies BEFORE the kernel launch (needed wherever launches block the calling thread:
  * kernel-replay profilers; CUDA_LAUNCH_BLOCKING=1 is detected by itself); bit 3 keeps the two-stage gradient exchange on 2
- * GPUs (default there: cluster shares stored straight into the peer's memory).  Measurement knobs for the runs under profiles/.
+ * GPUs (default there: cluster shares stored straight into the peer's memory); bit 4 sends pinned host images of
+ * pcnn_learn_host through the staged copy stream instead of letting the kernel pull them.  Measurement knobs for the runs
+ * under profiles/.
  * out6[5] of pcnn_persist_info: bit 0 = cooperative launch, bit 1 = direct exchange used. */
 int pcnn_persist_info(pcnn_ctx *ctx, int *out6);
 int pcnn_persist_tune(pcnn_ctx *ctx, int max_cluster);

@@ -594,6 +594,72 @@ static int ensure_host_stream(pcnn_ctx *ctx, size_t image_bytes, long labels, lo
     return PCNN_OK;
 }
 
+// pinned per-step result buffer (the kernel writes every step's error sum straight into it)
+static int ensure_step_err_host(pcnn_ctx *ctx, long total_steps) {
+    if (total_steps <= ctx->h_step_err_cap) return PCNN_OK;
+    PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_step_err) cudaFreeHost(ctx->h_step_err);
+    ctx->h_step_err = nullptr;
+    ctx->h_step_err_cap = 0;
+    PCNN_CUDA(cudaMallocHost((void **)&ctx->h_step_err, (size_t)total_steps * sizeof(float)));
+    ctx->h_step_err_cap = total_steps;
+    return PCNN_OK;
+}
+
+// Results (per-step sums, total, completion tag) arrive in pinned host memory straight from the kernel: poll the tag instead of
+// paying a stream synchronisation; the stream is queried now and then so that an aborted or failed launch cannot hang the host.
+static int wait_done_tag(pcnn_ctx *ctx, unsigned done_tag) {
+    volatile unsigned *tagp = reinterpret_cast<volatile unsigned *>(ctx->h_hs_done + 1);
+    bool seen = false;
+    for (unsigned long spins = 0;; ++spins) {
+        if (*tagp == done_tag) { seen = true; break; }
+        if ((spins & 4095) == 4095) {
+            const cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaSuccess) { seen = (*tagp == done_tag); break; }
+            if (q != cudaErrorNotReady) return pcnn_fail_cuda(q, "persistent training kernel", __FILE__, __LINE__);
+        }
+    }
+    if (!seen) {
+        PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
+        int rc;
+        if ((rc = pcnn_persist_check(ctx))) return rc;
+        PCNN_REQUIRE(*tagp == done_tag, PCNN_ERR_STATE, "pcnn_learn_host: the training kernel ended without reporting completion");
+    }
+    return PCNN_OK;
+}
+
+// Page-locked, device-mapped host images (cudaHostAlloc / cudaHostRegister; torch pin_memory): NO staging copy at all.  The
+// training kernel's own bulk copies (cp.async.bulk, one 784-pixel image per CTA and step, issued a step ahead) read the pinned
+// buffer across PCIe through its device alias, so a step's pixels cross the link exactly once, when a CTA asks for them, and
+// the host enqueues one label copy and one launch per epoch -- no chunks, no flags, no copy-engine work to interleave.
+static int learn_host_pull(pcnn_ctx *ctx, const void *images_alias, int pixel_type, const uint8_t *host_labels, long n, int B, int epochs,
+                           float *mean_err_out) {
+    int rc;
+    if ((rc = ensure_host_stream(ctx, 0, n, 0))) return rc;
+    const long steps = (n + B - 1) / B;
+    if ((rc = ensure_step_err_host(ctx, steps))) return rc;
+    PCNN_CUDA(cudaMemcpyAsync(ctx->d_hs_labels, host_labels, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));   // 1 byte per image
+    pcnn_split_binding tmp;
+    tmp.images = images_alias;
+    tmp.labels = ctx->d_hs_labels;
+    tmp.pixel_type = pixel_type;
+    tmp.n = n;
+    tmp.rank_local = true;
+    for (int ep = 0; ep < epochs; ++ep) {
+        const bool last = ep + 1 == epochs;
+        unsigned done_tag = 0;
+        if (last) {
+            done_tag = ++ctx->hs_serial;
+            if (done_tag == 0) done_tag = ++ctx->hs_serial;
+        }
+        if ((rc = pcnn_persist_run(ctx, tmp, B, steps, nullptr, ctx->h_step_err, 3, last ? ctx->h_hs_done : nullptr, done_tag))) return rc;
+        if (last && (rc = wait_done_tag(ctx, done_tag))) return rc;
+    }
+    ctx->step_err_count = steps;
+    if (mean_err_out) *mean_err_out = (float)(ctx->h_hs_done[0] / ((double)n * ctx->world));   // the all-reduced sum of the last epoch
+    return PCNN_OK;
+}
+
 static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel_type, const uint8_t *host_labels, long n, int B,
                                int epochs, float *mean_err_out) {
     const size_t px = (pixel_type == PCNN_F32 ? 4 : 1);
@@ -617,15 +683,7 @@ static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel
     const long max_chunks = (long)pcnn_chunk_of(ch, seg_samples > 0 ? seg_samples - 1 : 0) + 1;
     int rc;
     if ((rc = ensure_host_stream(ctx, (size_t)seg_samples * img_bytes, seg_samples, max_chunks))) return rc;
-    const long total_steps = (n + B - 1) / B;
-    if (total_steps > ctx->h_step_err_cap) {
-        PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (ctx->h_step_err) cudaFreeHost(ctx->h_step_err);
-        ctx->h_step_err = nullptr;
-        ctx->h_step_err_cap = 0;
-        PCNN_CUDA(cudaMallocHost((void **)&ctx->h_step_err, (size_t)total_steps * sizeof(float)));
-        ctx->h_step_err_cap = total_steps;
-    }
+    if ((rc = ensure_step_err_host(ctx, (n + B - 1) / B))) return rc;
     const char *hi = reinterpret_cast<const char *>(host_images);
     const bool resident_after_first = seg_samples >= n;      // later epochs re-use the staged copy
     double err = 0.0;
@@ -684,24 +742,7 @@ static int learn_host_streamed(pcnn_ctx *ctx, const void *host_images, int pixel
             }
             steps_done += steps;
             if (last) {
-                // Results (per-step sums, total, completion tag) arrive in pinned host memory straight from the kernel: poll
-                // the tag instead of paying a stream synchronisation; the stream is queried now and then so that an aborted
-                // or failed launch cannot hang the host.
-                volatile unsigned *tagp = reinterpret_cast<volatile unsigned *>(ctx->h_hs_done + 1);
-                bool seen = false;
-                for (unsigned long spins = 0;; ++spins) {
-                    if (*tagp == done_tag) { seen = true; break; }
-                    if ((spins & 4095) == 4095) {
-                        const cudaError_t q = cudaStreamQuery(ctx->stream);
-                        if (q == cudaSuccess) { seen = (*tagp == done_tag); break; }
-                        if (q != cudaErrorNotReady) return pcnn_fail_cuda(q, "persistent training kernel", __FILE__, __LINE__);
-                    }
-                }
-                if (!seen) {
-                    PCNN_CUDA(cudaStreamSynchronize(ctx->stream));
-                    if ((rc = pcnn_persist_check(ctx))) return rc;
-                    PCNN_REQUIRE(*tagp == done_tag, PCNN_ERR_STATE, "pcnn_learn_host: the training kernel ended without reporting completion");
-                }
+                if ((rc = wait_done_tag(ctx, done_tag))) return rc;
                 err = ctx->h_hs_done[0];
             } else if (off + sn < n || !resident_after_first) {
                 // the staging buffer is about to be refilled: wait for the kernel
@@ -723,8 +764,16 @@ extern "C" int pcnn_learn_host(pcnn_ctx *ctx, const void *host_images, int pixel
     pcnn_device_guard g(ctx->device);
     if (ctx->step_mode == PCNN_MODE_PERSISTENT)
         PCNN_REQUIRE(use_persistent(ctx), PCNN_ERR_STATE, "persistent mode requested but peers are not attached");
-    if (use_persistent(ctx))
+    if (use_persistent(ctx)) {
+        // pinned + mapped + 16-byte aligned images: the kernel pulls them itself; pageable memory goes through the staged stream
+        cudaPointerAttributes at{};
+        const cudaError_t pe = cudaPointerGetAttributes(&at, host_images);
+        if (pe != cudaSuccess) cudaGetLastError();
+        if (pe == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer && ((uintptr_t)at.devicePointer & 15) == 0 &&
+            !ctx->hs_no_pull)
+            return learn_host_pull(ctx, at.devicePointer, pixel_type, host_labels, n, B, epochs, mean_err_out);
         return learn_host_streamed(ctx, host_images, pixel_type, host_labels, n, B, epochs, mean_err_out);
+    }
     return learn_host_chunked(ctx, host_images, pixel_type, host_labels, n, B, epochs, mean_err_out);
 }
 

@@ -97,6 +97,7 @@ struct pcnn_ctx {
     long hs_label_cap = 0, hs_ready_cap = 0;
     unsigned hs_serial = 0;
     bool hs_copies_first = false;           // launches block the host thread (CUDA_LAUNCH_BLOCKING, kernel-replay profilers)
+    bool hs_no_pull = false;          // pcnn_persist_tune bit 4: pinned host images go through the staged stream too (A/B)
     double *h_hs_done = nullptr;            // pinned {double error sum, unsigned tag} written by the kernel after its last step
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};

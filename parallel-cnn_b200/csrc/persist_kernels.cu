@@ -337,6 +337,20 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         fetch_params_cluster<InT, CS>(S, a.params_ll, tag, crank, (unsigned)s & 1u, a.abort_flag);
         PCNN_TRACE2(1);
 
+        // The NEXT step's first image is requested now, a whole step ahead, when nothing gates it (device-resident data, or
+        // pinned host memory read across PCIe by this very copy: ~2 us of link latency disappear behind the step) and the
+        // other staging buffer is free (one image per CTA and step; with more, the in-step prefetch chain owns it)
+        const bool early_issue = a.ready == nullptr && nb <= G;
+        if (early_issue && t == 0 && s + 1 < a.nsteps) {
+            long long ecur = cursor + stride;
+            if (ecur >= a.n_total) ecur = 0;
+            long long ebase;
+            int enb;
+            shard(ecur, ebase, enb);
+            if (c < enb) issue_image(S, (c < nb ? li + 1 : li) & 1, images + (ebase + c) * PCNN_IMG);
+        }
+        __syncwarp();
+
         // ---- 2. forward + backward over this CTA's images, 3. CTA reduction, pieces pushed to the cluster ranks
         li = step_images<InT, CS>(S, id, images + base * PCNN_IMG, a.labels + base, c, G, nb, li, crank,
                                   tr0, tr1);
@@ -368,7 +382,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         int nnb;
         shard(ncur, nbase, nnb);
         const bool more = s + 1 < a.nsteps;
-        if (t == 0 && more && c < nnb) {
+        if (t == 0 && more && c < nnb && !early_issue) {
             const InT *src = images + (nbase + c) * PCNN_IMG;
             gate(src);
             issue_image(S, li & 1, src);
@@ -834,13 +848,14 @@ extern "C" int pcnn_persist_info(pcnn_ctx *ctx, int *out6) {
 
 extern "C" int pcnn_persist_tune(pcnn_ctx *ctx, int max_cluster) {
     PCNN_REQUIRE(ctx, PCNN_ERR_ARG, "pcnn_persist_tune: ctx is NULL");
-    PCNN_REQUIRE(max_cluster >= 0 && max_cluster <= 15, PCNN_ERR_ARG,
+    PCNN_REQUIRE(max_cluster >= 0 && max_cluster <= 31, PCNN_ERR_ARG,
                  "pcnn_persist_tune: bit mask of 1 (no clusters), 2 (clusters without the cooperative attribute), 4 (host copies before the "
-                 "launch), 8 (two-stage exchange also on 2..4 GPUs)");
+                 "launch), 8 (two-stage exchange also on 2 GPUs), 16 (pinned host images are staged, not pulled by the kernel)");
     ctx->persist_no_direct = (max_cluster & 8) != 0;
     ctx->persist_force_cluster = (max_cluster & 1) ? 1 : 0;
     if (max_cluster & 2) ctx->persist_no_coop = true;
     if (max_cluster & 4) ctx->hs_copies_first = true;
+    ctx->hs_no_pull = (max_cluster & 16) != 0;
     return PCNN_OK;
 }
 

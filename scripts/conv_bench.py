@@ -107,3 +107,27 @@ if only in ("all", "cfg5"):
     for N in (1, 8, 32, 128):
         run("224x224x3->64x3x3 bf16 (config 5)", N, 224, 224, 3, 64, 3, 3, 0, 10)
 eng.close()
+if only == "wprobe":                                                   # what a pure WRITE stream / pure READ stream / copy reach on this GPU
+    # library fill / reduce / copy kernels as a yardstick for the store-dominated forward pass (807 MB written, 39 MB read):
+    # MEASURED_PEAKS.json's HBM number is a COPY (half reads, half writes)
+    nbytes = 807 << 20
+    buf = torch.empty((nbytes // 4,), dtype=torch.int32, device="cuda")
+    src = torch.ones((nbytes // 4,), dtype=torch.int32, device="cuda")
+    def timeit(fn, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    ms_fill = timeit(lambda: buf.fill_(7))
+    ms_memset = timeit(lambda: buf.zero_())
+    ms_copy = timeit(lambda: buf.copy_(src))
+    ms_read = timeit(lambda: src.sum())
+    print(json.dumps({"case": "write/read/copy yardsticks (torch library kernels, 807 MiB)", "fill_GBps": nbytes / ms_fill / 1e6,
+                      "memset_GBps": nbytes / ms_memset / 1e6, "copy_GBps_read_plus_write": 2 * nbytes / ms_copy / 1e6,
+                      "reduce_read_GBps": nbytes / ms_read / 1e6, "hbm_peak_file": HBM}), flush=True)

@@ -19,7 +19,9 @@ eng = pkg.Engine(0)
 B = 256
 rng = np.random.default_rng(3)
 rows = []
-for steps in (1, 2, 5, 20, 80, 400):
+mode = sys.argv[1] if len(sys.argv) > 1 else "pull"     # "pull": the kernel reads the pinned buffer itself; "staged": copy stream
+eng.persist_tune(16 if mode == "staged" else 0)
+for steps in (1, 2, 5, 20, 80, 400, 4000):
     n = steps * B
     hi = torch.empty((n, 784), dtype=torch.uint8, pin_memory=True)
     hl = torch.empty((n,), dtype=torch.uint8, pin_memory=True)
@@ -37,7 +39,7 @@ for steps in (1, 2, 5, 20, 80, 400):
         t2 = time.perf_counter()
         ts.append((t1 - t0, t2 - t0))
     a = np.array(ts) * 1e6
-    rows.append({"steps": steps, "call_us_median": float(np.median(a[:, 0])), "call_plus_sync_us_median": float(np.median(a[:, 1])),
+    rows.append({"mode": mode, "steps": steps, "call_us_median": float(np.median(a[:, 0])), "call_plus_sync_us_median": float(np.median(a[:, 1])),
                  "call_us_min": float(a[:, 0].min()), "images_per_s_at_median": n / (np.median(a[:, 1]) * 1e-6)})
     print(json.dumps(rows[-1]), flush=True)
 x = np.array([r["steps"] for r in rows], float)

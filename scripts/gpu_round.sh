@@ -22,6 +22,8 @@ for f in ("bench_20", "bench", "bench_ref"):
     except Exception as e:
         print(f, "no json", e)
 PY
+echo "== LeNet-5-style variant"; timeout 300 python scripts/l5_bench.py > $OUT/l5_bench.jsonl 2> $OUT/l5_bench.err; cat $OUT/l5_bench.jsonl | cut -c1-160; tail -2 $OUT/l5_bench.err
+echo "== write/read yardsticks"; timeout 200 python scripts/conv_bench.py wprobe 2>&1 | tail -1 | tee $OUT/hbm_yardsticks.json
 if [ "${NCU:-0}" = "1" ]; then
   echo "== ncu launch list (default bench command)"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv \

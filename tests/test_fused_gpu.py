@@ -145,6 +145,45 @@ def test_host_entry_points_match_device_path(eng, pkg, golden, data):
     assert abs(e - err_ref) <= 1e-5 * err_ref
 
 
+@pytest.mark.parametrize("B,n", [(128, 1000), (1, 37), (256, 1024), (512, 900)])
+def test_pinned_host_images_are_pulled_by_the_kernel_and_match_the_staged_path(eng, pkg, golden, data, B, n):
+    """pcnn_learn_host with page-locked images: the training kernel reads them across PCIe itself (no staging copy); pageable
+    images go through the staged copy stream.  Same samples, same order -> bit-identical parameters and per-step errors, also
+    against the device-resident path; two epochs re-read the host buffer."""
+    import torch
+    imgs, labs = data["train"][:n], data["labels"][:n]
+    eng.dataset_upload(pkg.TRAIN_SET, imgs, labs)
+    eng.set_params(golden["params_init"])
+    e_dev = eng.learn(B=B, epochs=2)
+    p_dev = eng.get_params()
+    hi = torch.empty((n, 784), dtype=torch.uint8, pin_memory=True)
+    hl = torch.empty((n,), dtype=torch.uint8, pin_memory=True)
+    hi.numpy()[:] = imgs
+    hl.numpy()[:] = labs
+    eng.set_params(golden["params_init"])
+    e_pull = eng.learn_host(hi.numpy(), hl.numpy(), B=B, epochs=2)
+    errs_pull = eng.step_errs().copy()
+    assert np.array_equal(p_dev.view(np.uint32), eng.get_params().view(np.uint32))
+    assert abs(e_dev - e_pull) < 1e-6
+    eng.set_params(golden["params_init"])
+    e_staged = eng.learn_host(np.array(imgs, copy=True), np.array(labs, copy=True), B=B, epochs=2)     # pageable
+    assert np.array_equal(p_dev.view(np.uint32), eng.get_params().view(np.uint32))
+    assert np.array_equal(errs_pull.view(np.uint32), eng.step_errs().view(np.uint32)) and abs(e_pull - e_staged) < 1e-6
+    eng.persist_tune(16)                                # pinned memory through the staged stream (the A/B knob)
+    try:
+        eng.set_params(golden["params_init"])
+        eng.learn_host(hi.numpy(), hl.numpy(), B=B, epochs=2)
+        assert np.array_equal(p_dev.view(np.uint32), eng.get_params().view(np.uint32))
+    finally:
+        eng.persist_tune(0)
+    # fp32 pixels, pinned
+    hf = torch.empty((n, 784), dtype=torch.float32, pin_memory=True)
+    hf.numpy()[:] = data["train_f32"][:n]
+    eng.set_params(golden["params_init"])
+    eng.learn_host(hf.numpy(), hl.numpy(), B=B, epochs=2)
+    assert np.array_equal(p_dev.view(np.uint32), eng.get_params().view(np.uint32))
+
+
 def test_forward_batch_and_classify(eng, pkg, golden, data):
     p = golden["params_after1000"]
     eng.set_params(p)
