@@ -180,6 +180,12 @@ int pcnn_measure_fp32_peak(pcnn_ctx *ctx, float *tflops_out);
  * 1 pixel x 32 rows), 3 = the weight-gradient kernel's pattern (one row of pixels per box).  The ceiling the convolution
  * backward kernels are measured against next to the HBM copy peak. */
 int pcnn_measure_tma_read(pcnn_ctx *ctx, const void *dev_bf16, int N, int P, int Q, int mode, int iters, float *gbps_out);
+/* store rate (GB/s) of the forward convolution's epilogue with everything but the stores removed: y viewed as [N][P][row_elems]
+ * bf16, tiles of 128 rows x 256 columns walked like the forward kernel (image height H on the input side, H % 32 == 0).  mode 0 =
+ * the kernel's own pattern (boxes {64 columns, 32 rows}, 128-byte swizzle), 1 / 2 = boxes of 128 / 256 columns without swizzle,
+ * 3 = per-row 1-D bulk stores of 128 bytes, 4 = four boxes per commit group; hot = 1 aims every tile at the first row block (an
+ * L2-resident target).  The ceiling the forward kernel's store phase is measured against. */
+int pcnn_measure_tma_write(pcnn_ctx *ctx, void *dev_bf16, int N, int P, int H, int row_elems, int mode, int hot, int iters, float *gbps_out);
 /* SM clocks per tcgen05.mma (kind::f16 bf16, K = 16, shape M x N, operands K- or MN-major in shared memory) when one thread
  * issues `reps` of them back to back over `nacc` rotating accumulators: the issue-rate table the convolution kernels are
  * designed against (small-N instructions are far from the tensor-pipe peak). */

@@ -90,6 +90,7 @@ _SIG = {
     "pcnn_time_fused_kernel": [_vp, _i, _i, C.POINTER(_f)],
     "pcnn_measure_fp32_peak": [_vp, C.POINTER(_f)],
     "pcnn_measure_tma_read": [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(_f)],
+    "pcnn_measure_tma_write": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, C.POINTER(_f)],
     "pcnn_measure_mma_rate": [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(_f)],
     "pcnn_comm_unique_id": [_vp, C.POINTER(_sz)],
     "pcnn_comm_init_rank": [_vp, _vp, _i, _i],

@@ -28,6 +28,10 @@
 
 using namespace pcnn_tc;
 
+#ifndef PCNN_DBG_CONV
+#define PCNN_DBG_CONV 0        // 1, 2, 3: measurement builds of the forward kernel (see the epilogue); never shipped
+#endif
+
 namespace {
 
 constexpr int TC_THREADS = 320;         // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
@@ -82,6 +86,28 @@ static size_t conv_tc_smem_bytes(int V, int R, int ncols, int stages) {
     return (size_t)V * R * ncols * TC_KCHUNK * 2 + (size_t)stages * R * A_TILE_BYTES + TC_EPI_WARPS * OUT_STAGE_BYTES + sizeof(ConvTcCtl) + 1024;
 }
 
+// Explicit shared-space accesses for the epilogue.  Through generic pointers the compiler must assume that the staging-buffer
+// stores alias the bias table, so every group of 8 outputs waited for its own bias load (ncu: 32 % of the stall samples on the
+// FADDs behind LD.E.128; ~3,500 cycles per tile).  Non-volatile ld.shared can be hoisted and kept in registers.
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u4(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+template <int N> __device__ __forceinline__ void load_bias_regs(float (&b)[N], uint32_t addr) {
+#pragma unroll
+    for (int j = 0; j < N; j += 4) {
+        const float4 q = lds_f4(addr + j * 4);
+        b[j] = q.x; b[j + 1] = q.y; b[j + 2] = q.z; b[j + 3] = q.w;
+    }
+}
+
+// ACT (0 none, 1 sigmoid), BIAS and the store path are compile-time: the epilogue is straight-line code per variant (as
+// run-time flags they were re-tested for every group of 8 outputs)
+template <int ACT, bool BIAS, bool TMA_ST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b,
               const __grid_constant__ CUtensorMap map_y, const ConvTcParams p) {
@@ -120,7 +146,7 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 const int stage = it % NST;
                 const unsigned ph = (unsigned)(it / NST) & 1u;
-                bar_wait(&S.empty[stage], ph ^ 1u);
+                bar_wait_relaxed(&S.empty[stage], ph ^ 1u, 32);   // NST stages of slack: no need to spin on the MMA warp's sub-partition
                 const int mt = tile / p.n_qtiles, qt = tile % p.n_qtiles;
                 bar_expect_tx(&S.full[stage], (unsigned)(p.R * A_TILE_BYTES));
                 for (int r = 0; r < p.R; ++r)
@@ -166,6 +192,13 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const int quarter = warp & 3;                           // TMEM lanes this warp may read
         const int colhalf = (warp - 2) >> 2;                    // two warps share a lane quarter: even / odd column boxes
         unsigned char *obuf = sv.out(warp - 2);                 // 2 x 4 KB, 1024-byte aligned
+        const uint32_t obuf_s = s_u32(obuf), bias_s = s_u32(S.bias);
+        const uint32_t lane_row = (uint32_t)lane * 128u, lane_sw = (uint32_t)lane & 7u;
+        // TMA-store path: the warp's 64 columns of an iteration are colhalf * 64 + 128 i + [0, 64).  The bias table repeats with
+        // period K, so when K divides 128 the 64 values are the same in every iteration and tile: they live in registers
+        const bool bias_inv = (128 % p.K) == 0;
+        float bz[64];
+        if (TMA_ST && BIAS && bias_inv) load_bias_regs(bz, bias_s + colhalf * 64 * 4);
         int ob = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -174,21 +207,28 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             const int mt = tile / p.n_qtiles, qt = tile % p.n_qtiles;
             bar_wait(&S.tfull[acc], aph);
             tc_fence_after();
+#if PCNN_DBG_CONV == 3      // measurement build: the epilogue only hands the accumulator back (load + MMA pipeline alone)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) bar_arrive(&S.tempty[acc]);
+            continue;
+#endif
             const int q0 = qt * p.Qt;
             int valid_cols = (p.Q - q0) * p.K;
             if (valid_cols > p.ncols) valid_cols = p.ncols;
-            if (p.tma_store) {
+            if (TMA_ST) {
                 const long long m0 = (long long)mt * TC_M + quarter * 32;      // first row of this warp: n * H + p
                 const int n = (int)(m0 / p.H), pr = (int)(m0 % p.H);           // H % 32 == 0: the 32 rows share n
                 const bool group_ok = n < p.n_img && pr < p.P;
                 for (int col0 = colhalf * 64; col0 < p.ncols; col0 += 128) {
-                    unsigned char *buf = obuf + ob * 4096;
+                    const uint32_t buf = obuf_s + ob * 4096;
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // buffer `ob` is free again
                     __syncwarp();
                     uint32_t vv[2][32];
                     const uint32_t tbase = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + col0);
                     tc_ld_32x32(tbase, vv[0]);                                   // both halves in flight, one wait
                     if (col0 + 32 < p.ncols) tc_ld_32x32(tbase + 32, vv[1]);
+                    if (BIAS && !bias_inv) load_bias_regs(bz, bias_s + col0 * 4);   // behind the TMEM loads' latency
                     tc_wait_ld();
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
@@ -200,8 +240,9 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                                 float f[8];
 #pragma unroll
                                 for (int u = 0; u < 8; ++u) {
-                                    f[u] = __uint_as_float(v[j + u]) + S.bias[c0 + j + u];
-                                    if (p.act == 1) f[u] = __fdividef(1.0f, 1.0f + __expf(-f[u]));
+                                    f[u] = __uint_as_float(v[j + u]);
+                                    if (BIAS) f[u] += bz[half * 32 + j + u];
+                                    if (ACT == 1) f[u] = __fdividef(1.0f, 1.0f + __expf(-f[u]));
                                 }
                                 uint4 o;
                                 __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
@@ -209,16 +250,26 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                                 o.x = *reinterpret_cast<uint32_t *>(&t0); o.y = *reinterpret_cast<uint32_t *>(&t1);
                                 o.z = *reinterpret_cast<uint32_t *>(&t2); o.w = *reinterpret_cast<uint32_t *>(&t3);
                                 const int chunk = half * 4 + (j >> 3);                     // 16-byte chunk of the 128-byte row
-                                *reinterpret_cast<uint4 *>(buf + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
+                                sts_u4(buf + lane_row + ((chunk ^ lane_sw) << 4), o);
                             }
                         }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy writes -> TMA reads
                     __syncwarp();
+#if PCNN_DBG_CONV == 1      // measurement build: no global stores at all
+                    if (false) {
+#else
                     if (lane == 0 && group_ok && col0 < valid_cols) {
+#endif
+#if PCNN_DBG_CONV == 2      // measurement build: every store lands on the first row block (L2-resident target)
                         asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map_y),
-                                     "r"(q0 * p.K + col0), "r"(pr), "r"(n), "r"(s_u32(buf))
+                                     "r"(q0 * p.K + col0), "r"(pr % 32), "r"(0), "r"(buf)
                                      : "memory");
+#else
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map_y),
+                                     "r"(q0 * p.K + col0), "r"(pr), "r"(n), "r"(buf)
+                                     : "memory");
+#endif
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ob ^= 1;
@@ -231,6 +282,8 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 for (int c0 = colhalf * 32; c0 < p.ncols; c0 += 64) {
                     uint32_t v[32];
                     tc_ld_32x32(tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256 + c0), v);
+                    float b32[32];
+                    if (BIAS) load_bias_regs(b32, bias_s + c0 * 4);
                     tc_wait_ld();
                     if (row_ok) {
 #pragma unroll
@@ -239,8 +292,9 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                             float f[8];
 #pragma unroll
                             for (int u = 0; u < 8; ++u) {
-                                f[u] = __uint_as_float(v[j + u]) + S.bias[c0 + j + u];
-                                if (p.act == 1) f[u] = __fdividef(1.0f, 1.0f + __expf(-f[u]));
+                                f[u] = __uint_as_float(v[j + u]);
+                                if (BIAS) f[u] += b32[j + u];
+                                if (ACT == 1) f[u] = __fdividef(1.0f, 1.0f + __expf(-f[u]));
                             }
                             if (c0 + j + 8 <= valid_cols && ((reinterpret_cast<uintptr_t>(yrow + c0 + j) & 15) == 0)) {
                                 uint4 o;
@@ -260,7 +314,7 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             __syncwarp();
             if (lane == 0) bar_arrive(&S.tempty[acc]);
         }
-        if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed
+        if (TMA_ST && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores landed
         __syncwarp();
     }
     tc_fence_before();
@@ -269,6 +323,14 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
     }
+}
+
+typedef void (*conv_tc_fwd_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvTcParams);
+static const void *conv_tc_fwd_variant(bool sigmoid, bool bias, bool tma_store) {
+    static const conv_tc_fwd_fn table[8] = {
+        k_conv_tc_fwd<0, false, false>, k_conv_tc_fwd<1, false, false>, k_conv_tc_fwd<0, true, false>, k_conv_tc_fwd<1, true, false>,
+        k_conv_tc_fwd<0, false, true>,  k_conv_tc_fwd<1, false, true>,  k_conv_tc_fwd<0, true, true>,  k_conv_tc_fwd<1, true, true>};
+    return reinterpret_cast<const void *>(table[(sigmoid ? 1 : 0) | (bias ? 2 : 0) | (tma_store ? 4 : 0)]);
 }
 
 // fp32 [rows][w] -> bf16 [rows][pitch] (zero padded), for building the padded NHWC activations the TMA map needs
@@ -413,7 +475,9 @@ extern "C" int pcnn_conv_tc_plan_create_strided(pcnn_ctx *ctx, int N, int H, int
     if (rc) return rc;
     static bool configured[64] = {};        // function attributes are per device
     if (!configured[ctx->device & 63]) {
-        PCNN_CUDA(cudaFuncSetAttribute(k_conv_tc_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BUDGET + 2048));
+        for (int v = 0; v < 8; ++v)
+            PCNN_CUDA(cudaFuncSetAttribute(conv_tc_fwd_variant(v & 1, (v >> 1) & 1, (v >> 2) & 1), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           TC_SMEM_BUDGET + 2048));
         configured[ctx->device & 63] = true;
     }
     guard.p = nullptr;
@@ -448,7 +512,9 @@ extern "C" int pcnn_conv_tc_fwd(pcnn_ctx *ctx, pcnn_conv_plan *plan, const void 
     }
     const int ntiles = p.n_mtiles * p.n_qtiles;
     const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
-    k_conv_tc_fwd<<<grid, TC_THREADS, conv_tc_smem_bytes(p.V, p.R, p.ncols, p.stages), ctx->stream>>>(map_x, plan->map_b, map_y, p);
+    void *args[] = {&map_x, &plan->map_b, &map_y, &p};
+    PCNN_CUDA(cudaLaunchKernel(conv_tc_fwd_variant(p.act == 1, p.bias != nullptr, p.tma_store != 0), dim3((unsigned)grid), dim3(TC_THREADS), args,
+                               conv_tc_smem_bytes(p.V, p.R, p.ncols, p.stages), ctx->stream));
     PCNN_CHECK_LAUNCH(ctx);
     return PCNN_OK;
 }

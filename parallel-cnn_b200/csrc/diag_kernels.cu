@@ -151,6 +151,158 @@ extern "C" int pcnn_measure_tma_read(pcnn_ctx *ctx, const void *dev_bf16, int N,
     return PCNN_OK;
 }
 
+namespace {
+
+// ---- TMA store probe --------------------------------------------------------------------------------------------------
+// How fast can the store half of the convolution forward epilogue run with everything else removed?  Output y viewed as
+// [N][P][row_elems] bf16 (the forward kernel's own view); the grid walks tiles of 128 rows x 256 columns exactly like the
+// forward kernel and every epilogue warp issues the stores of its rows from a (never written) shared-memory staging buffer:
+//   mode 0: the forward kernel's pattern: 8 warps x 2 boxes {64 cols, 32 rows, 1 image}, SWIZZLE_128B (4 KB per instruction)
+//   mode 1: 4 warps x 2 boxes {128 cols, 32 rows}, SWIZZLE_NONE (8 KB per instruction, 256-byte rows)
+//   mode 2: 4 warps x 1 box {256 cols, 32 rows}, SWIZZLE_NONE (16 KB per instruction, 512-byte rows)
+//   mode 3: mode 0 with every lane issuing 1-D bulk stores of its own 128-byte row piece (no tensor map)
+//   mode 4: 4 warps x 4 boxes {64 cols, 32 rows} issued back to back by one lane, then one commit (group of 16 KB)
+// `hot` = 1 makes every tile land on the first row block (an L2-resident target instead of HBM).
+struct StoreParams {
+    int mode, hot, n_img, P, H, n_mtiles, n_qtiles, row_elems;
+    unsigned char *y;
+};
+
+__global__ void __launch_bounds__(256, 1) k_tma_store_probe(const __grid_constant__ CUtensorMap map, const StoreParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = p.n_mtiles * p.n_qtiles;
+    const int quarter = warp & 3, colhalf = warp >> 2;
+    unsigned char *obuf = base + (size_t)warp * 32768;           // up to 2 x 16 KB per warp
+    int ob = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int mt = tile / p.n_qtiles, qt = tile % p.n_qtiles;
+        const long long m0 = (long long)mt * 128 + quarter * 32;
+        int n = (int)(m0 / p.H), pr = (int)(m0 % p.H);
+        const bool ok = n < p.n_img && pr < p.P;
+        if (p.hot) { n = 0; pr = pr % 32; }
+        const int c_tile = qt * 256;
+        if (p.mode == 0 || p.mode == 3) {
+            for (int col0 = colhalf * 64; col0 < 256; col0 += 128) {
+                const uint32_t buf = s_u32(obuf + ob * 4096);
+                if (p.mode == 0) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && ok) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map),
+                                     "r"(c_tile + col0), "r"(pr), "r"(n), "r"(buf) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                } else {
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    if (ok && pr + lane < p.P && c_tile + col0 + 64 <= p.row_elems) {
+                        unsigned char *dst = p.y + (((long long)n * p.P + pr + lane) * p.row_elems + c_tile + col0) * 2;
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(dst), "r"(buf + lane * 128) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                ob ^= 1;
+            }
+        } else if (p.mode == 1) {
+            if (colhalf == 0)
+                for (int col0 = 0; col0 < 256; col0 += 128) {
+                    const uint32_t buf = s_u32(obuf + ob * 8192);
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0 && ok) {
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map),
+                                     "r"(c_tile + col0), "r"(pr), "r"(n), "r"(buf) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ob ^= 1;
+                }
+        } else if (p.mode == 2) {
+            if (colhalf == 0) {
+                const uint32_t buf = s_u32(obuf + ob * 16384);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                if (lane == 0 && ok) {
+                    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map),
+                                 "r"(c_tile), "r"(pr), "r"(n), "r"(buf) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                ob ^= 1;
+            }
+        } else {
+            if (colhalf == 0) {
+                const uint32_t buf = s_u32(obuf + ob * 16384);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                if (lane == 0 && ok) {
+                    for (int b = 0; b < 4; ++b)
+                        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(&map),
+                                     "r"(c_tile + b * 64), "r"(pr), "r"(n), "r"(buf + b * 4096) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                ob ^= 1;
+            }
+        }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+}  // namespace
+
+extern "C" int pcnn_measure_tma_write(pcnn_ctx *ctx, void *dev_bf16, int N, int P, int H, int row_elems, int mode, int hot, int iters,
+                                      float *gbps_out) {
+    PCNN_REQUIRE(ctx && dev_bf16 && gbps_out && N > 0 && P > 0 && H >= P && H % 32 == 0 && row_elems > 0 && row_elems % 8 == 0 && mode >= 0 &&
+                     mode <= 4 && iters > 0,
+                 PCNN_ERR_ARG, "pcnn_measure_tma_write: bad argument");
+    PCNN_REQUIRE(((uintptr_t)dev_bf16 & 15) == 0, PCNN_ERR_ARG, "pcnn_measure_tma_write: tensor must be 16-byte aligned");
+    pcnn_device_guard g(ctx->device);
+    StoreParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode = mode; p.hot = hot; p.n_img = N; p.P = P; p.H = H; p.row_elems = row_elems;
+    p.n_mtiles = (int)(((long long)N * H + 127) / 128);
+    p.n_qtiles = (row_elems + 255) / 256;
+    p.y = reinterpret_cast<unsigned char *>(dev_bf16);
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    const uint64_t dims[3] = {(uint64_t)row_elems, (uint64_t)P, (uint64_t)N};
+    const uint64_t str[2] = {(uint64_t)row_elems * 2, (uint64_t)row_elems * 2 * P};
+    const uint32_t cols = mode == 1 ? 128 : (mode == 2 ? 256 : 64);
+    const uint32_t box[3] = {cols, 32, 1};
+    int rc = make_map_bf16(&map, dev_bf16, 3, dims, str, box, cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc) return rc;
+    const size_t smem = 8 * 32768 + 1024;
+    static bool configured[64] = {};
+    if (!configured[ctx->device & 63]) {
+        PCNN_CUDA(cudaFuncSetAttribute(k_tma_store_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[ctx->device & 63] = true;
+    }
+    struct Events {
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } ev;
+    PCNN_CUDA(cudaEventCreate(&ev.a));
+    PCNN_CUDA(cudaEventCreate(&ev.b));
+    const int ntiles = p.n_mtiles * p.n_qtiles;
+    const int grid = ntiles < ctx->sm_count ? ntiles : ctx->sm_count;
+    for (int i = 0; i < 2; ++i) {
+        k_tma_store_probe<<<grid, 256, smem, ctx->stream>>>(map, p);
+        PCNN_CHECK_LAUNCH(ctx);
+    }
+    PCNN_CUDA(cudaEventRecord(ev.a, ctx->stream));
+    for (int i = 0; i < iters; ++i) {
+        k_tma_store_probe<<<grid, 256, smem, ctx->stream>>>(map, p);
+        PCNN_CHECK_LAUNCH(ctx);
+    }
+    PCNN_CUDA(cudaEventRecord(ev.b, ctx->stream));
+    PCNN_CUDA(cudaEventSynchronize(ev.b));
+    float ms = 0.0f;
+    PCNN_CUDA(cudaEventElapsedTime(&ms, ev.a, ev.b));
+    const double bytes = (double)N * P * row_elems * 2.0;        // the bytes of y (every one written once per launch when hot == 0)
+    *gbps_out = (float)(bytes * iters / (ms * 1e-3) / 1e9);
+    return PCNN_OK;
+}
+
 // ---- tcgen05.mma issue/throughput probe -------------------------------------------------------------------------------
 // One CTA, one issuing thread: `reps` back-to-back tcgen05.mma (kind::f16, K = 16) on zero operands, rotating over `nacc`
 // accumulators, then one commit; reports SM clocks per MMA.  The convolution kernels size their MMAs against this table.

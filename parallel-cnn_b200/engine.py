@@ -293,6 +293,11 @@ class Engine:
         self._call("pcnn_measure_tma_read", _p(dev_bf16), int(N), int(P), int(Q), int(mode), int(iters), C.byref(t))
         return t.value
 
+    def measure_tma_write(self, dev_bf16, N, P, H, row_elems, mode, hot=0, iters=10):
+        t = C.c_float()
+        self._call("pcnn_measure_tma_write", _p(dev_bf16), int(N), int(P), int(H), int(row_elems), int(mode), int(hot), int(iters), C.byref(t))
+        return t.value
+
     # ------------------------------------------------------------------ data parallel
     @staticmethod
     def comm_unique_id():

@@ -24,12 +24,12 @@ rng = np.random.default_rng(1234)
 only = sys.argv[1] if len(sys.argv) > 1 else "all"
 
 
-def run(name, N, H, W, C, K, R, S, act, iters, image_rows=0):
+def run(name, N, H, W, C, K, R, S, act, iters, image_rows=0, bias=True):
     pitch = (W * C + 7) // 8 * 8
     P, Q = H - R + 1, W - S + 1
     f = rng.uniform(-0.5, 0.5, (K, R, S, C)).astype(np.float32)
     b = rng.uniform(-0.5, 0.5, K).astype(np.float32)
-    plan = pkg.ConvPlan(eng, N, H, W, C, K, R, S, f, b, act=act, row_pitch=pitch, image_rows=image_rows)
+    plan = pkg.ConvPlan(eng, N, H, W, C, K, R, S, f, b if bias else None, act=act, row_pitch=pitch, image_rows=image_rows)
     x = torch.randint(0, 0x3F80, (N * (image_rows or H), pitch), dtype=torch.int16, device="cuda")   # positive bf16 bit patterns < 1.0
     y = torch.empty((N, P, Q, K), dtype=torch.int16, device="cuda")
     for _ in range(3):
@@ -103,6 +103,21 @@ if only == "lenet1024":                                                # BASELIN
     run("lenet_c1_bf16_sigmoid (config 3 shape)", 1024, 28, 28, 1, 6, 5, 5, 1, 2)
 if only == "fwd128":                                                   # the profiler's target
     run("224x224x3->64x3x3 bf16 (config 5)", 128, 224, 224, 3, 64, 3, 3, 0, 2)
+if only == "stprobe":                                                  # the store phase of the forward epilogue alone
+    N, P, H, RE = 128, 222, 224, 222 * 64
+    y = torch.empty((N, P, RE), dtype=torch.int16, device="cuda")
+    for mode in range(5):
+        for hot in (0, 1):
+            g = eng.measure_tma_write(y, N, P, H, RE, mode, hot, 10)
+            print(json.dumps({"case": "tma store probe", "mode": mode, "hot_l2_target": hot, "GBps": g, "us_per_launch": N * P * RE * 2 / g / 1e3}), flush=True)
+if only == "fwdq":                                                     # one line: forward at N = 128 without bias
+    run("224x224x3->64x3x3 bf16 (config 5), no bias", 128, 224, 224, 3, 64, 3, 3, 0, 20, bias=False)
+if only == "fwdab":                                                    # forward at N = 128: with / without bias, with sigmoid
+    run("224x224x3->64x3x3 bf16 (config 5), bias", 128, 224, 224, 3, 64, 3, 3, 0, 20)
+    run("224x224x3->64x3x3 bf16 (config 5), no bias", 128, 224, 224, 3, 64, 3, 3, 0, 20, bias=False)
+    run("224x224x3->64x3x3 bf16 (config 5), bias + sigmoid", 128, 224, 224, 3, 64, 3, 3, 1, 20)
+    run("lenet_c1_bf16_sigmoid, 32-row image pitch (TMA-store epilogue)", 65536, 28, 28, 1, 6, 5, 5, 1, 20, image_rows=32)
+    run("lenet_c1_bf16_sigmoid (config 3 shape)", 65536, 28, 28, 1, 6, 5, 5, 1, 20)
 if only in ("all", "cfg5"):
     for N in (1, 8, 32, 128):
         run("224x224x3->64x3x3 bf16 (config 5)", N, 224, 224, 3, 64, 3, 3, 0, 10)
