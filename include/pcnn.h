@@ -183,7 +183,8 @@ int pcnn_measure_tma_read(pcnn_ctx *ctx, const void *dev_bf16, int N, int P, int
 /* store rate (GB/s) of the forward convolution's epilogue with everything but the stores removed: y viewed as [N][P][row_elems]
  * bf16, tiles of 128 rows x 256 columns walked like the forward kernel (image height H on the input side, H % 32 == 0).  mode 0 =
  * the kernel's own pattern (boxes {64 columns, 32 rows}, 128-byte swizzle), 1 / 2 = boxes of 128 / 256 columns without swizzle,
- * 3 = per-row 1-D bulk stores of 128 bytes, 4 = four boxes per commit group; hot = 1 aims every tile at the first row block (an
+ * 3 = per-row 1-D bulk stores of 128 bytes, 4 = four boxes per commit group, 5 = 32-byte st.global.v8 from registers (no TMA),
+ * 6 = half TMA boxes, half direct stores; hot = 1 aims every tile at the first row block (an
  * L2-resident target).  The ceiling the forward kernel's store phase is measured against. */
 int pcnn_measure_tma_write(pcnn_ctx *ctx, void *dev_bf16, int N, int P, int H, int row_elems, int mode, int hot, int iters, float *gbps_out);
 /* SM clocks per tcgen05.mma (kind::f16 bf16, K = 16, shape M x N, operands K- or MN-major in shared memory) when one thread

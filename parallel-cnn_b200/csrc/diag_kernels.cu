@@ -162,6 +162,8 @@ namespace {
 //   mode 2: 4 warps x 1 box {256 cols, 32 rows}, SWIZZLE_NONE (16 KB per instruction, 512-byte rows)
 //   mode 3: mode 0 with every lane issuing 1-D bulk stores of its own 128-byte row piece (no tensor map)
 //   mode 4: 4 warps x 4 boxes {64 cols, 32 rows} issued back to back by one lane, then one commit (group of 16 KB)
+//   mode 5: no TMA: every lane writes its row's 128-byte piece with four 32-byte st.global.v8 (SASS STG.256), 8 warps
+//   mode 6: half and half: the even column boxes by TMA (mode 0), the odd ones by direct 32-byte stores (mode 5)
 // `hot` = 1 makes every tile land on the first row block (an L2-resident target instead of HBM).
 struct StoreParams {
     int mode, hot, n_img, P, H, n_mtiles, n_qtiles, row_elems;
@@ -174,7 +176,8 @@ __global__ void __launch_bounds__(256, 1) k_tma_store_probe(const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = p.n_mtiles * p.n_qtiles;
     const int quarter = warp & 3, colhalf = warp >> 2;
-    unsigned char *obuf = base + (size_t)warp * 32768;           // up to 2 x 16 KB per warp
+    // modes 0, 1, 3: 2 x (4 or 8) KB per warp; modes 2, 4: 2 x 16 KB for each of the four issuing warps (128 KB in all)
+    unsigned char *obuf = base + (size_t)warp * (p.mode == 2 || p.mode == 4 ? 32768 : 16384);
     int ob = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int mt = tile / p.n_qtiles, qt = tile % p.n_qtiles;
@@ -183,10 +186,20 @@ __global__ void __launch_bounds__(256, 1) k_tma_store_probe(const __grid_constan
         const bool ok = n < p.n_img && pr < p.P;
         if (p.hot) { n = 0; pr = pr % 32; }
         const int c_tile = qt * 256;
-        if (p.mode == 0 || p.mode == 3) {
+        if (p.mode == 5 || (p.mode == 6 && colhalf == 1)) {
+            // direct path: every lane owns a row and writes its 128-byte piece as four 32-byte (full-sector) stores from registers
+            if (ok && pr + lane < p.P)
+                for (int col0 = colhalf * 64; col0 < 256; col0 += 128) {
+                    if (c_tile + col0 + 64 > p.row_elems) continue;
+                    unsigned char *dst = p.y + (((long long)n * p.P + pr + lane) * p.row_elems + c_tile + col0) * 2;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        asm volatile("st.global.v8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(dst + k * 32), "r"(tile + k) : "memory");
+                }
+        } else if (p.mode == 0 || p.mode == 3 || p.mode == 6) {
             for (int col0 = colhalf * 64; col0 < 256; col0 += 128) {
                 const uint32_t buf = s_u32(obuf + ob * 4096);
-                if (p.mode == 0) {
+                if (p.mode != 3) {
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     __syncwarp();
                     if (lane == 0 && ok) {
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(256, 1) k_tma_store_probe(const __grid_constan
 extern "C" int pcnn_measure_tma_write(pcnn_ctx *ctx, void *dev_bf16, int N, int P, int H, int row_elems, int mode, int hot, int iters,
                                       float *gbps_out) {
     PCNN_REQUIRE(ctx && dev_bf16 && gbps_out && N > 0 && P > 0 && H >= P && H % 32 == 0 && row_elems > 0 && row_elems % 8 == 0 && mode >= 0 &&
-                     mode <= 4 && iters > 0,
+                     mode <= 6 && iters > 0,
                  PCNN_ERR_ARG, "pcnn_measure_tma_write: bad argument");
     PCNN_REQUIRE(((uintptr_t)dev_bf16 & 15) == 0, PCNN_ERR_ARG, "pcnn_measure_tma_write: tensor must be 16-byte aligned");
     pcnn_device_guard g(ctx->device);
@@ -271,7 +284,7 @@ extern "C" int pcnn_measure_tma_write(pcnn_ctx *ctx, void *dev_bf16, int N, int 
     int rc = make_map_bf16(&map, dev_bf16, 3, dims, str, box, cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_NONE);
     if (rc) return rc;
-    const size_t smem = 8 * 32768 + 1024;
+    const size_t smem = 128 * 1024 + 1024;
     static bool configured[64] = {};
     if (!configured[ctx->device & 63]) {
         PCNN_CUDA(cudaFuncSetAttribute(k_tma_store_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
