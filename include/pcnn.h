@@ -156,7 +156,10 @@ int pcnn_compute_grads(pcnn_ctx *ctx, const void *dev_images, int pixel_type, co
 /* learn(): `epochs` passes over the bound train split in dataset order with batch B (tail batch kept);
  * mean_err_out = sum of error norms / n of the LAST epoch, as learn() prints  [ref: Main.cpp:146-184] */
 int pcnn_learn(pcnn_ctx *ctx, int B, int epochs, float *mean_err_out);
-/* same, streaming the dataset from host memory through a double-buffered H2D pipeline */
+/* same, with the dataset in HOST memory.  Page-locked images (cudaHostAlloc / cudaHostRegister, 16-byte aligned): the training
+ * kernel reads them across PCIe itself, one image per CTA and step, a step ahead -- no staging copy, one label copy + one launch
+ * per epoch.  Pageable images: staged through a chunked H2D copy stream that the kernel follows chunk by chunk.  Same samples,
+ * same order, bit-identical results either way; returns when the last step's results are in host memory. */
 int pcnn_learn_host(pcnn_ctx *ctx, const void *host_images, int pixel_type, const uint8_t *host_labels,
                     long n, int B, int epochs, float *mean_err_out);
 int pcnn_err_sum(pcnn_ctx *ctx, double *sum_out, int reset);           /* running sum of per-sample error norms */
