@@ -97,6 +97,14 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 __device__ __forceinline__ void sts_u4(uint32_t addr, const uint4 &v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
+// sigmoid for a bf16 result: 0.5 + 0.5 tanh(x / 2) with ONE transcendental (MUFU.TANH) instead of two (EX2 + RCP) -- the
+// epilogue of a sigmoid layer is bound by the 16-lane MUFU pipe.  tanh.approx is good to ~5e-4 absolute, a quarter of a bf16 ulp
+// of the result; the test bound (2^-8 |ref| + 1e-3) is unchanged.
+__device__ __forceinline__ float sigmoid_bf16(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(t, 0.5f, 0.5f);
+}
 template <int N> __device__ __forceinline__ void load_bias_regs(float (&b)[N], uint32_t addr) {
 #pragma unroll
     for (int j = 0; j < N; j += 4) {
@@ -242,7 +250,7 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                                 for (int u = 0; u < 8; ++u) {
                                     f[u] = __uint_as_float(v[j + u]);
                                     if (BIAS) f[u] += bz[half * 32 + j + u];
-                                    if (ACT == 1) f[u] = __fdividef(1.0f, 1.0f + __expf(-f[u]));
+                                    if (ACT == 1) f[u] = sigmoid_bf16(f[u]);
                                 }
                                 uint4 o;
                                 __nv_bfloat162 t0 = __floats2bfloat162_rn(f[0], f[1]), t1 = __floats2bfloat162_rn(f[2], f[3]);
@@ -294,7 +302,7 @@ k_conv_tc_fwd(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                             for (int u = 0; u < 8; ++u) {
                                 f[u] = __uint_as_float(v[j + u]);
                                 if (BIAS) f[u] += b32[j + u];
-                                if (ACT == 1) f[u] = __fdividef(1.0f, 1.0f + __expf(-f[u]));
+                                if (ACT == 1) f[u] = sigmoid_bf16(f[u]);
                             }
                             if (c0 + j + 8 <= valid_cols && ((reinterpret_cast<uintptr_t>(yrow + c0 + j) & 15) == 0)) {
                                 uint4 o;
