@@ -470,8 +470,8 @@ def run_ours(a):
         bound = same * 1e9 / 785.0 * world
         link = {"h2d_GBps_64MB": big, "h2d_GBps_same_bytes_one_copy": same, "link_bound_images_per_s": bound,
                 "e2e_frac_of_link_bound": e2e_val / bound,
-                "note": "one cudaMemcpyAsync of the e2e call's input bytes, nothing else: no training step can start before "
-                        "its pixels have crossed this link"}
+                "note": "one cudaMemcpyAsync of the e2e call's input bytes, nothing else: the rate at which this box's link can "
+                        "deliver pixels; every step needs B x 785 of them"}
     barrier()
 
     # ---- BASELINE.json configs[3]: 1024 images per GPU (weak) and a fixed global batch of 8192 (strong)
@@ -566,7 +566,7 @@ def run_ours(a):
                        "l2": f"inputs larger than L2: steps walk a {n_data}-image ({n_data * 784 / 1e6:.0f} MB) device-resident set",
                        "update": "w += (dt / global_batch) * sum_b g_b, dt = 0.1 (equals the reference at batch 1)"},
             "e2e": {"value": e2e_val, "unit": "images/s", "h2d_bytes_per_step": B * 785 * world,
-                    "d2h_bytes_per_step": 4 * world, "steps": K2, "api": "Engine.learn_host (pcnn_learn_host), pinned host u8",
+                    "d2h_bytes_per_step": 4 * world, "steps": K2, "api": "Engine.learn_host (pcnn_learn_host), pinned host u8: the training kernel pulls each step's images across PCIe itself (cp.async.bulk from the pinned buffer); labels by one H2D copy; per-step results written to mapped host memory",
                     "link": link},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "ref_gpu_baseline": ref_gpu, "clocks": clocks,
             "parity": parity, "batch1024": b1024, "phase_trace": phases, "conv": conv,
