@@ -641,6 +641,7 @@ static int learn_host_pull(pcnn_ctx *ctx, const void *images_alias, int pixel_ty
     PCNN_CUDA(cudaMemcpyAsync(ctx->d_hs_labels, host_labels, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));   // 1 byte per image
     pcnn_split_binding tmp;
     tmp.images = images_alias;
+    tmp.host_resident = true;
     tmp.labels = ctx->d_hs_labels;
     tmp.pixel_type = pixel_type;
     tmp.n = n;

@@ -34,6 +34,7 @@ struct pcnn_split_binding {
     void *owned_images = nullptr;           // non-null when uploaded through pcnn_dataset_upload
     void *owned_labels = nullptr;
     bool rank_local = false;                // true: this rank's private shard (no rank offset into it)
+    bool host_resident = false;             // images are the device alias of pinned HOST memory (pcnn_learn_host pulls them)
 };
 
 // where one step takes its samples from

@@ -45,6 +45,7 @@ struct PersistArgs {
     const unsigned *ready;
     unsigned ready_tag;
     pcnn_chunking ready_chunks;   // sample -> chunk (pcnn_chunk_of)
+    int early;                // 1: request the next step's first image a whole step ahead (images read across PCIe)
     int fresh;                // bit 0: start at sample 0 / step 0 instead of the device-side counters; bit 1: err_total = 0
     float *step_err_host;     // optional mapped pinned array [nsteps]: per-step error sums written straight to the host
     double *done_host;        // optional mapped pinned {double error sum, unsigned tag}: written after the LAST step, so the
@@ -244,7 +245,9 @@ __device__ __forceinline__ int step_images(FusedSmem<InT> &S, const ThreadId &id
     return li;
 }
 
-template <typename InT, int CS>
+// DIRECT (2 GPUs, see PersistArgs::xslots) is compile-time: as a run-time flag the generalised slot addressing of the owner gather
+// cost every configuration 0.65 us per step (8.49 -> 9.13 us on one GPU, scripts/step_ab_raw.py).
+template <typename InT, int CS, bool DIRECT>
 __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const PersistArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem<InT> &S = *reinterpret_cast<FusedSmem<InT> *>(smem_raw);
@@ -273,7 +276,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
     const int cnt = e0 >= NPACK ? 0 : (e0 + chunk > NPACK ? NPACK - e0 : chunk);
     const int PH = chunk >= NT ? 1 : NT / chunk;         // slot phases when the chunk is narrower than the CTA
     constexpr int KB = 8;                                // slot words one thread keeps in flight
-    const int NV = a.direct ? NC * a.world : NC;         // slots an owner gathers: clusters (x ranks with the direct exchange)
+    const int NV = DIRECT ? NC * a.world : NC;           // slots an owner gathers: clusters (x ranks with the direct exchange)
     const int PHG = PH < (NV + KB - 1) / KB ? PH : (NV + KB - 1) / KB;   // phases in use: thread (e, ph) adds slots ph, ph + PHG, ...
 
     long long cursor = (a.fresh & 1) ? 0 : *a.cursor;
@@ -337,10 +340,10 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         fetch_params_cluster<InT, CS>(S, a.params_ll, tag, crank, (unsigned)s & 1u, a.abort_flag);
         PCNN_TRACE2(1);
 
-        // The NEXT step's first image is requested now, a whole step ahead, when nothing gates it (device-resident data, or
-        // pinned host memory read across PCIe by this very copy: ~2 us of link latency disappear behind the step) and the
-        // other staging buffer is free (one image per CTA and step; with more, the in-step prefetch chain owns it)
-        const bool early_issue = a.ready == nullptr && nb <= G;
+        // Images in pinned HOST memory (pcnn_learn_host): the NEXT step's first image is requested now, a whole step ahead, so that
+        // the ~2 us of PCIe latency disappear behind the step; the other staging buffer is free (one image per CTA and step;
+        // with more, the in-step prefetch chain owns it).  Device-resident data keep the late request (0.08 us per step cheaper).
+        const bool early_issue = a.early != 0 && nb <= G;
         if (early_issue && t == 0 && s + 1 < a.nsteps) {
             long long ecur = cursor + stride;
             if (ecur >= a.n_total) ecur = 0;
@@ -365,7 +368,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
 #pragma unroll
                 for (int q = 0; q < CS; ++q) g += S.recv[q * Share<CS>::SH + i];
                 ll_store(cslot + my_sb + i, g, tag);
-                if (a.direct) {          // the peers' owners gather this cluster's share straight from their own memory
+                if (DIRECT) {            // the peers' owners gather this cluster's share straight from their own memory
                     const unsigned xt = a.xstep_base + (unsigned)s + 1u;
                     const long long off = ((((long long)(xt & 1u) * PCNN_MAX_PEERS + a.rank) * XS_MAXC + (CS == 1 ? c : (int)cluster_idx())) * NPACK) + my_sb + i;
                     for (int r = 0; r < a.world; ++r)
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
         const unsigned xtag = a.xstep_base + (unsigned)s + 1u;
         // entry p: local sum g, parameter value before the step w_old; returns the updated parameter
         auto finalize = [&](int p, float g, float w_old) -> float {
-            if (a.world > 1 && !a.direct) {
+            if (a.world > 1 && !DIRECT) {
                 // "low-latency" push: every 8-byte inbox word carries {value, step id}; one NVLink one-way latency per step.
                 // Every polling round then requests the words of ALL ranks still missing at once; the ranks' values are
                 // added in rank order, so all GPUs compute bit-identical sums.
@@ -444,43 +447,68 @@ __global__ void __launch_bounds__(NT, FUSED_CTAS_PER_SM) k_train_persist(const P
             const int e = t % chunk, ph = t / chunk;
             float sum = 0.0f;
             if (e < cnt && ph < PHG) {
-                // virtual slot v = (source rank, cluster): this GPU's own clusters live in slots_ll (local tag), the peers' in
-                // xslots (exchange tag); every GPU adds them in the same (rank, cluster) order -> bit-identical replicas
-                const int par = (int)(xtag & 1u);
-                auto slot_word = [&](int v, const llword *&ptr, unsigned &want, bool &remote) {
-                    const int q = v / NC, k = v - q * NC;
-                    remote = a.direct && q != a.rank;
-                    ptr = remote ? a.xslots + ((((long long)par * PCNN_MAX_PEERS + q) * XS_MAXC + k) * NPACK) + e0 + e
-                                 : a.slots_ll + (long long)k * NPACK + e0 + e;
-                    want = remote ? xtag : tag;
-                };
                 PollGuard guard(a.abort_flag, &S.aborted);
-                for (int k0 = ph; k0 < NV; k0 += KB * PHG) {
-                    float v[KB];
-                    unsigned pend = 0;
+                if (DIRECT) {
+                    // virtual slot v = (source rank, cluster): this GPU's own clusters live in slots_ll (local tag), the peers' in
+                    // xslots (exchange tag); every GPU adds them in the same (rank, cluster) order -> bit-identical replicas
+                    const int par = (int)(xtag & 1u);
+                    auto slot_word = [&](int v, const llword *&ptr, unsigned &want, bool &remote) {
+                        const int q = v / NC, k = v - q * NC;
+                        remote = q != a.rank;
+                        ptr = remote ? a.xslots + ((((long long)par * PCNN_MAX_PEERS + q) * XS_MAXC + k) * NPACK) + e0 + e
+                                     : a.slots_ll + (long long)k * NPACK + e0 + e;
+                        want = remote ? xtag : tag;
+                    };
+                    for (int k0 = ph; k0 < NV; k0 += KB * PHG) {
+                        float v[KB];
+                        unsigned pend = 0;
 #pragma unroll
-                    for (int u = 0; u < KB; ++u) {
-                        v[u] = 0.0f;
-                        if (k0 + u * PHG < NV) pend |= 1u << u;
+                        for (int u = 0; u < KB; ++u) {
+                            v[u] = 0.0f;
+                            if (k0 + u * PHG < NV) pend |= 1u << u;
+                        }
+                        while (pend) {
+                            unsigned g[KB], want[KB];
+#pragma unroll
+                            for (int u = 0; u < KB; ++u)
+                                if ((pend >> u) & 1u) {
+                                    const llword *ptr;
+                                    bool remote;
+                                    slot_word(k0 + u * PHG, ptr, want[u], remote);
+                                    if (remote) ll_load_sys(ptr, v[u], g[u]);
+                                    else ll_load(ptr, v[u], g[u]);
+                                }
+#pragma unroll
+                            for (int u = 0; u < KB; ++u)
+                                if (((pend >> u) & 1u) && g[u] == want[u]) pend &= ~(1u << u);
+                            if (pend && guard.expired(1)) break;
+                        }
+#pragma unroll
+                        for (int u = 0; u < KB; ++u) sum += v[u];              // slot order within the phase
                     }
-                    while (pend) {
-                        unsigned g[KB], want[KB];
+                } else {
+                    const llword *sp = a.slots_ll + e0 + e;
+                    for (int k0 = ph; k0 < NC; k0 += KB * PHG) {
+                        float v[KB];
+                        unsigned pend = 0;
 #pragma unroll
-                        for (int u = 0; u < KB; ++u)
-                            if ((pend >> u) & 1u) {
-                                const llword *ptr;
-                                bool remote;
-                                slot_word(k0 + u * PHG, ptr, want[u], remote);
-                                if (remote) ll_load_sys(ptr, v[u], g[u]);
-                                else ll_load(ptr, v[u], g[u]);
-                            }
+                        for (int u = 0; u < KB; ++u) {
+                            v[u] = 0.0f;
+                            if (k0 + u * PHG < NC) pend |= 1u << u;
+                        }
+                        while (pend) {
+                            unsigned g[KB];
 #pragma unroll
-                        for (int u = 0; u < KB; ++u)
-                            if (((pend >> u) & 1u) && g[u] == want[u]) pend &= ~(1u << u);
-                        if (pend && guard.expired(1)) break;
+                            for (int u = 0; u < KB; ++u)
+                                if ((pend >> u) & 1u) ll_load(sp + (long long)(k0 + u * PHG) * NPACK, v[u], g[u]);
+#pragma unroll
+                            for (int u = 0; u < KB; ++u)
+                                if (((pend >> u) & 1u) && g[u] == tag) pend &= ~(1u << u);
+                            if (pend && guard.expired(1)) break;
+                        }
+#pragma unroll
+                        for (int u = 0; u < KB; ++u) sum += v[u];              // slot order within the phase
                     }
-#pragma unroll
-                    for (int u = 0; u < KB; ++u) sum += v[u];                  // slot order within the phase
                 }
             }
             if (ph < PHG) S.part[ph * chunk + e] = sum;
@@ -529,7 +557,8 @@ constexpr int PERSIST_CS = 8;            // cluster size of the dataflow kernel 
 
 template <typename InT> int persist_cap(int *out) {
     int m = 1 << 30;
-    const void *fns[2] = {(const void *)k_train_persist<InT, PERSIST_CS>, (const void *)k_train_persist<InT, 1>};
+    const void *fns[3] = {(const void *)k_train_persist<InT, PERSIST_CS, false>, (const void *)k_train_persist<InT, PERSIST_CS, true>,
+                          (const void *)k_train_persist<InT, 1, false>};
     for (const void *fn : fns) {
         int per_sm = 0;
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FusedSmem<InT>));
@@ -555,7 +584,7 @@ template <typename InT> int cluster_cap(int sm_count) {
     cfg.attrs = at;
     cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, k_train_persist<InT, PERSIST_CS>, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&n, k_train_persist<InT, PERSIST_CS, false>, &cfg) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -654,6 +683,7 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
             a.ready_tag = gate->tag;
             a.ready_chunks = gate->chunks;
         }
+        a.early = (s.host_resident && !gate) ? 1 : 0;
         a.fresh = fresh;
         fresh = 0;                                                 // a split longer than one launch continues
         a.step_err_host = step_err_host;
@@ -675,10 +705,12 @@ int pcnn_persist_run(pcnn_ctx *ctx, const pcnn_split_binding &s, int B, long nst
             a.direct = (ctx->world >= 2 && ctx->world <= PCNN_DIRECT_MAX_WORLD && cs > 1 && grid / cs <= XS_MAXC && grid > 16 &&
                         !ctx->persist_no_direct) ? 1 : 0;
             const void *fn;
-            if (cs > 1)
-                fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist<uint8_t, PERSIST_CS> : (const void *)k_train_persist<float, PERSIST_CS>;
+            if (cs > 1 && a.direct)
+                fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist<uint8_t, PERSIST_CS, true> : (const void *)k_train_persist<float, PERSIST_CS, true>;
+            else if (cs > 1)
+                fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist<uint8_t, PERSIST_CS, false> : (const void *)k_train_persist<float, PERSIST_CS, false>;
             else
-                fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist<uint8_t, 1> : (const void *)k_train_persist<float, 1>;
+                fn = s.pixel_type == PCNN_U8 ? (const void *)k_train_persist<uint8_t, 1, false> : (const void *)k_train_persist<float, 1, false>;
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)grid);
             cfg.blockDim = dim3(NT);
