@@ -15,7 +15,7 @@ fi
 for MODE in ${MODES:-persistent graph}; do
   echo "== bench N=$N mode=$MODE"
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700 + RANDOM % 200)) \
-      bench.py --gpus $N --steps ${STEPS:-2000} --warmup ${WARMUP:-100} --mode $MODE --persist-tune ${TUNE:-0} --no-cpu-baseline > $OUT/bench_n${N}_$MODE.json 2> $OUT/bench_n${N}_$MODE.err
+      bench.py --gpus $N --steps ${STEPS:-2000} --warmup ${WARMUP:-100} --mode $MODE --persist-tune ${TUNE:-0} --no-cpu-baseline ${EXTRA:-} > $OUT/bench_n${N}_$MODE.json 2> $OUT/bench_n${N}_$MODE.err
   echo "rc=$?"; python - <<PY
 import json
 try:
