@@ -188,7 +188,8 @@ int pcnn_measure_tma_read(pcnn_ctx *ctx, const void *dev_bf16, int N, int P, int
  * the kernel's own pattern (boxes {64 columns, 32 rows}, 128-byte swizzle), 1 / 2 = boxes of 128 / 256 columns without swizzle,
  * 3 = per-row 1-D bulk stores of 128 bytes, 4 = four boxes per commit group, 5 = 32-byte st.global.v8 from registers (no TMA),
  * 6 = half TMA boxes, half direct stores; hot = 1 aims every tile at the first row block (an
- * L2-resident target).  The ceiling the forward kernel's store phase is measured against. */
+ * L2-resident target).  The ceiling the forward kernel's store phase is measured against.  The tensor is OVERWRITTEN with
+ * unspecified values (the staging buffers are never filled). */
 int pcnn_measure_tma_write(pcnn_ctx *ctx, void *dev_bf16, int N, int P, int H, int row_elems, int mode, int hot, int iters, float *gbps_out);
 /* SM clocks per tcgen05.mma (kind::f16 bf16, K = 16, shape M x N, operands K- or MN-major in shared memory) when one thread
  * issues `reps` of them back to back over `nacc` rotating accumulators: the issue-rate table the convolution kernels are
